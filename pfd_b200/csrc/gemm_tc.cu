@@ -1,0 +1,511 @@
+// tcgen05 tensor-core contraction for sm_100a: one persistent, warp-specialised kernel that serves
+// every Linear / 1x1 conv / 3x3 conv (implicit GEMM; TMA performs the im2col gather with
+// zero-filled halos) / batched QK^T and PV product on the Prompt-Free-Diffusion hot path.
+//
+//   D[128 x BN] (fp32, TMEM)  +=  A[128 x 64] (fp16, smem, TMA 4-D box)  x  B[BN x 64]^T (fp16, smem)
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = epilogue
+// (TMEM -> registers -> fused bias / time-embedding / activation / GEGLU / residual -> global).
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
+// tile i+1.  See include/pfd_b200.h (pfd_gemm_f16) for the reference call sites this replaces.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/pfd_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pfd {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int STAGE_A_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int SMEM_BUDGET = 232448;         // 227 KiB opt-in limit per CTA
+
+struct alignas(64) GemmParams {
+  CUtensorMap tmA[PFD_MAX_SEG];
+  CUtensorMap tmB;
+  int nseg;
+  int taps[PFD_MAX_SEG];
+  int chunks[PFD_MAX_SEG];
+  int a_c[PFD_MAX_SEG];
+  int stride;
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_nb, n_tiles;
+  int W, H, NB, N;
+  int b_batched;
+  int num_kb;
+  float alpha;
+  int act;
+  const __half* bias;
+  const __half* rowadd;
+  const __half* residual;
+  __half* out;
+  long long so_n1, so_n0, so_y, so_x, so_c1, so_c0;
+  int ndiv, cdiv;
+  int vec_ok;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGE_B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+  static constexpr int RAW_STAGES = (SMEM_BUDGET - 1024 - 256) / STAGE_BYTES;
+  static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128u : (2 * BN <= 256 ? 256u : 512u);
+  static_assert(STAGE_B_BYTES % 1024 == 0, "B stage must keep 1024-B swizzle alignment");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == PFD_ACT_SILU) return v / (1.f + __expf(-v));
+  if (act == PFD_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (act == PFD_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+__device__ __forceinline__ void load8h(const __half* p, float (&f)[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const uint32_t smemA = base;
+  const uint32_t smemB = base + STAGES * STAGE_A_BYTES;
+  const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_g =
+      reinterpret_cast<volatile uint32_t*>(gbase + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_nb;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int tx = m_tile % p.tiles_w;
+        const int ty = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int x0 = tx * p.bw * p.stride;
+        const int y0 = ty * p.bh * p.stride;
+        const int n0 = tn * p.bn;
+        const int bcoord = p.b_batched ? n0 : 0;
+        int kofs = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int ntap = p.taps[s];
+          for (int t = 0; t < ntap; ++t) {
+            const int dy = (ntap == 9) ? (t / 3 - 1) : 0;
+            const int dx = (ntap == 9) ? (t % 3 - 1) : 0;
+            for (int j = 0; j < p.chunks[s]; ++j) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+              tma_load_4d(smemA + stage * STAGE_A_BYTES, &p.tmA[s], full_bar(stage), j * BK,
+                          x0 + dx, y0 + dy, n0);
+              tma_load_3d(smemB + stage * Cfg::STAGE_B_BYTES, &p.tmB, full_bar(stage),
+                          kofs + j * BK, n_tile * BN, bcoord);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+            kofs += p.a_c[s];
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_kmajor_desc(smemA + stage * STAGE_A_BYTES);
+          const uint64_t bdesc = make_sw128_kmajor_desc(smemB + stage * Cfg::STAGE_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 fp16 = 32 B inside the 128-B swizzle atom: +2 in the (addr>>4) field
+            umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rdx = row % p.bw;
+    const int rdy = (row / p.bw) % p.bh;
+    const int rdn = row / (p.bw * p.bh);
+    const bool geglu = (p.act == PFD_ACT_GEGLU);
+    const int n_out = geglu ? p.N / 2 : p.N;
+    constexpr int CB = BN;  // columns per tile in TMEM
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int tx = m_tile % p.tiles_w;
+      const int ty = (m_tile / p.tiles_w) % p.tiles_h;
+      const int tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int x = tx * p.bw + rdx;
+      const int y = ty * p.bh + rdy;
+      const int n = tn * p.bn + rdn;
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.NB);
+      const long long row_off = (long long)(n / p.ndiv) * p.so_n1 + (long long)(n % p.ndiv) * p.so_n0 +
+                                (long long)y * p.so_y + (long long)x * p.so_x;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * CB;
+      const int ocols = geglu ? CB / 2 : CB;             // output columns this tile produces
+      const int col_base = n_tile * ocols;               // first output column of the tile
+      for (int c0 = 0; c0 < ocols; c0 += 16) {
+        if (col_base + c0 >= n_out) break;               // warp-uniform
+        uint32_t r[16];
+        uint32_t g[16];
+        tmem_ld16(taddr + c0, r);
+        if (geglu) tmem_ld16(taddr + CB / 2 + c0, g);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int col = col_base + c0 + h8 * 8;
+          if (col >= n_out) break;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h8 * 8 + i]) * p.alpha;
+          if (geglu) {
+            float gt[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gt[i] = __uint_as_float(g[h8 * 8 + i]) * p.alpha;
+            if (p.bias) {
+              float bv[8], bg[8];
+              load8h(p.bias + (long long)n_tile * CB + c0 + h8 * 8, bv);
+              load8h(p.bias + (long long)n_tile * CB + CB / 2 + c0 + h8 * 8, bg);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[i] += bv[i];
+                gt[i] += bg[i];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              // reference rounds proj output to fp16 before the gate product (attention.py:50-51)
+              float a = __half2float(__float2half_rn(v[i]));
+              float b = __half2float(__float2half_rn(gt[i]));
+              float ge = 0.5f * b * (1.f + erff(b * 0.70710678118654752f));
+              v[i] = a * __half2float(__float2half_rn(ge));
+            }
+          } else {
+            if (p.bias) {
+              float bv[8];
+              load8h(p.bias + col, bv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += bv[i];
+            }
+            if (p.rowadd) {
+              float rv[8];
+              load8h(p.rowadd + (long long)n * p.N + col, rv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += rv[i];
+            }
+            if (p.act != PFD_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], p.act);
+            }
+          }
+          const long long coff = (long long)(col / p.cdiv) * p.so_c1 + (long long)(col % p.cdiv) * p.so_c0;
+          if (p.vec_ok) {
+            if (p.residual) {
+              float rv[8];
+              load8h(p.residual + row_off + coff, rv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += rv[i];
+            }
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(p.out + row_off + coff) = o;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = col + i;
+              const long long off =
+                  row_off + (long long)(c / p.cdiv) * p.so_c1 + (long long)(c % p.cdiv) * p.so_c0;
+              float t = v[i];
+              if (p.residual) t += __half2float(p.residual[off]);
+              p.out[off] = __float2half_rn(t);
+            }
+          }
+        }
+        }  // valid
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                      const cuuint32_t* estr, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return set_error(
+        "tensor map (%s) encode failed: CUresult %d rank %d dims[%llu,%llu,%llu,%llu] "
+        "strides[%llu,%llu,%llu] box[%u,%u,%u,%u] ptr %p",
+        what, (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+        (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+        (unsigned long long)strides_bytes[0], (unsigned long long)(rank > 2 ? strides_bytes[1] : 0),
+        (unsigned long long)(rank > 3 ? strides_bytes[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
+        rank > 3 ? box[3] : 0, ptr);
+  }
+  return 0;
+}
+
+static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
+
+template <int BN>
+static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  return check_launch("pfd_gemm_f16");
+}
+
+}  // namespace pfd
+
+using namespace pfd;
+
+extern "C" int pfd_gemm_f16(const pfd_gemm_desc* d) {
+  if (!d) return set_error("pfd_gemm_f16: null descriptor");
+  if (d->nseg < 1 || d->nseg > PFD_MAX_SEG) return set_error("pfd_gemm_f16: nseg %d out of range", d->nseg);
+  if (d->N <= 0 || d->N % 8) return set_error("pfd_gemm_f16: N=%d must be a positive multiple of 8", d->N);
+  if (d->K % 8) return set_error("pfd_gemm_f16: K pitch %lld must be a multiple of 8", (long long)d->K);
+  if (d->W <= 0 || d->H <= 0 || d->NB <= 0) return set_error("pfd_gemm_f16: empty output raster");
+  if (d->stride != 1 && d->stride != 2) return set_error("pfd_gemm_f16: stride %d unsupported", d->stride);
+  if (!d->out || !d->b_ptr) return set_error("pfd_gemm_f16: null out/b pointer");
+  long long ktot = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    if (d->taps[s] != 1 && d->taps[s] != 9) return set_error("pfd_gemm_f16: taps[%d]=%d", s, d->taps[s]);
+    if (d->a_c[s] <= 0 || d->a_c[s] % 8) return set_error("pfd_gemm_f16: a_c[%d]=%d must be a multiple of 8", s, d->a_c[s]);
+    if (!d->a_ptr[s]) return set_error("pfd_gemm_f16: a_ptr[%d] is null", s);
+    if ((reinterpret_cast<uintptr_t>(d->a_ptr[s]) & 15) || (d->a_sx[s] % 8) || (d->a_sy[s] % 8) || (d->a_sn[s] % 8))
+      return set_error("pfd_gemm_f16: A segment %d not 16-byte aligned/strided", s);
+    ktot += (long long)d->taps[s] * d->a_c[s];
+  }
+  if (ktot > d->K) return set_error("pfd_gemm_f16: segments cover K=%lld > pitch %lld", ktot, (long long)d->K);
+  if (reinterpret_cast<uintptr_t>(d->b_ptr) & 15) return set_error("pfd_gemm_f16: B not 16-byte aligned");
+  const bool geglu = d->act == PFD_ACT_GEGLU;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = d->nseg;
+  p.stride = d->stride;
+  p.W = d->W; p.H = d->H; p.NB = d->NB; p.N = d->N;
+  p.b_batched = d->b_batch_stride != 0;
+  p.alpha = d->alpha;
+  p.act = d->act;
+  p.bias = static_cast<const __half*>(d->bias);
+  p.rowadd = static_cast<const __half*>(d->rowadd);
+  p.residual = static_cast<const __half*>(d->residual);
+  p.out = static_cast<__half*>(d->out);
+  p.so_n1 = d->so_n1; p.so_n0 = d->so_n0; p.so_y = d->so_y; p.so_x = d->so_x;
+  p.so_c1 = d->so_c1; p.so_c0 = d->so_c0;
+  p.ndiv = d->ndiv > 0 ? d->ndiv : 1;
+  p.cdiv = d->cdiv > 0 ? d->cdiv : (1 << 30);
+  p.vec_ok = (d->so_c0 == 1) && (p.cdiv % 8 == 0) && (d->so_n1 % 8 == 0) && (d->so_n0 % 8 == 0) &&
+             (d->so_y % 8 == 0) && (d->so_x % 8 == 0) && (d->so_c1 % 8 == 0) &&
+             ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) &&
+             ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0);
+  if ((reinterpret_cast<uintptr_t>(d->bias) & 15) || (reinterpret_cast<uintptr_t>(d->rowadd) & 15))
+    return set_error("pfd_gemm_f16: bias/rowadd must be 16-byte aligned");
+
+  // ---- output raster tiling: 128 rows = bw x bh x bn pixels, minimise padded work
+  int bw = 128, bh = 1, bn = 1;
+  if (!p.b_batched) {
+    long long best = -1;
+    for (int cw = 128; cw >= 1; cw >>= 1) {
+      if (cw * d->stride > 256) continue;
+      for (int ch = 128 / cw; ch >= 1; ch >>= 1) {
+        if (ch * d->stride > 256) continue;
+        int cn = 128 / (cw * ch);
+        long long cost = cdivll(d->W, cw) * cdivll(d->H, ch) * cdivll(d->NB, cn);
+        if (best < 0 || cost < best) {
+          best = cost; bw = cw; bh = ch; bn = cn;
+        }
+      }
+    }
+  }
+  p.bw = bw; p.bh = bh; p.bn = bn;
+  p.tiles_w = (int)cdivll(d->W, bw);
+  p.tiles_h = (int)cdivll(d->H, bh);
+  p.tiles_nb = (int)cdivll(d->NB, bn);
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_nb;
+
+  // ---- N tile: minimise (waves x per-tile cost)
+  const int cands[5] = {256, 192, 160, 128, 64};
+  int BNsel = 128;
+  double best_cost = -1;
+  const int sms = num_sms();
+  for (int i = 0; i < 5; ++i) {
+    const int bn_c = cands[i];
+    if (geglu && (d->N % bn_c)) continue;
+    if (d->bn_force && d->bn_force != bn_c) continue;
+    const long long nt = cdivll(d->N, bn_c);
+    const long long tiles = m_tiles * nt;
+    const double waves = (double)cdivll(tiles, sms);
+    const double cost = waves * (bn_c + 24);
+    if (best_cost < 0 || cost < best_cost - 1e-9) {
+      best_cost = cost; BNsel = bn_c;
+    }
+  }
+  if (best_cost < 0) return set_error("pfd_gemm_f16: no valid N tile (bn_force=%d, N=%d, geglu=%d)", d->bn_force, d->N, (int)geglu);
+  p.n_tiles = (int)cdivll(d->N, BNsel);
+
+  // ---- tensor maps
+  int num_kb = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    p.taps[s] = d->taps[s];
+    p.a_c[s] = d->a_c[s];
+    p.chunks[s] = (d->a_c[s] + BK - 1) / BK;
+    num_kb += p.taps[s] * p.chunks[s];
+    cuuint64_t dims[4] = {(cuuint64_t)d->a_c[s], (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->NB};
+    cuuint64_t strides[3] = {(cuuint64_t)d->a_sx[s] * 2, (cuuint64_t)d->a_sy[s] * 2, (cuuint64_t)d->a_sn[s] * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * d->stride), (cuuint32_t)(bh * d->stride), (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    if (int rc = encode_map(&p.tmA[s], d->a_ptr[s], 4, dims, strides, box, estr, "A")) return rc;
+  }
+  p.num_kb = num_kb;
+  {
+    const long long nbatch = p.b_batched ? d->NB : 1;
+    cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)nbatch};
+    const long long bs = p.b_batched ? d->b_batch_stride : (long long)d->K * d->N;
+    cuuint64_t strides[2] = {(cuuint64_t)d->K * 2, (cuuint64_t)bs * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BNsel, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (int rc = encode_map(&p.tmB, d->b_ptr, 3, dims, strides, box, estr, "B")) return rc;
+  }
+
+  const long long total = m_tiles * p.n_tiles;
+  const int grid = (int)(total < sms ? total : sms);
+  cudaStream_t st = static_cast<cudaStream_t>(d->stream);
+  switch (BNsel) {
+    case 64: return launch_gemm<64>(p, grid, st);
+    case 128: return launch_gemm<128>(p, grid, st);
+    case 160: return launch_gemm<160>(p, grid, st);
+    case 192: return launch_gemm<192>(p, grid, st);
+    default: return launch_gemm<256>(p, grid, st);
+  }
+}

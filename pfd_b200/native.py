@@ -1,0 +1,414 @@
+"""ctypes binding of the C-ABI kernel library (``libpfd_b200.so``, see ``include/pfd_b200.h``).
+
+This is the *only* way compute reaches the GPU in this package: there is no torch / CPU fallback.
+If the shared library is missing or a call fails, a ``RuntimeError`` is raised.
+
+Tensors are torch CUDA fp16 tensors used purely as device-memory handles (``data_ptr()``); the
+stream is torch's current stream so calls can be captured into CUDA graphs.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpfd_b200.so")
+
+PFD_MAX_SEG = 3
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_RELU, ACT_GEGLU = 0, 1, 2, 3, 4
+
+EXPORTS = [
+    "pfd_version", "pfd_last_error", "pfd_launch_count", "pfd_gemm_f16", "pfd_groupnorm_f16",
+    "pfd_layernorm_f16", "pfd_softmax_f16", "pfd_timestep_embedding_f16", "pfd_upsample2x_f16",
+    "pfd_nchw_to_nhwc_f16", "pfd_nhwc_to_nchw_f16", "pfd_im2col3x3_f16", "pfd_axpby_f16",
+    "pfd_add_rowvec_f16", "pfd_ddim_step_f16", "pfd_window_gather_f16", "pfd_window_scatter_f16",
+    "pfd_patch_merge_gather_f16", "pfd_flash_attn_f16",
+]
+
+
+class GemmDesc(ctypes.Structure):
+    """Mirror of ``pfd_gemm_desc`` (include/pfd_b200.h)."""
+    _fields_ = [
+        ("nseg", c_int32),
+        ("taps", c_int32 * PFD_MAX_SEG),
+        ("a_c", c_int32 * PFD_MAX_SEG),
+        ("a_ptr", c_void_p * PFD_MAX_SEG),
+        ("a_sx", c_int64 * PFD_MAX_SEG),
+        ("a_sy", c_int64 * PFD_MAX_SEG),
+        ("a_sn", c_int64 * PFD_MAX_SEG),
+        ("in_w", c_int32), ("in_h", c_int32),
+        ("stride", c_int32),
+        ("W", c_int32), ("H", c_int32), ("NB", c_int32),
+        ("b_ptr", c_void_p),
+        ("N", c_int32),
+        ("K", c_int64),
+        ("b_batch_stride", c_int64),
+        ("alpha", c_float),
+        ("act", c_int32),
+        ("bias", c_void_p),
+        ("rowadd", c_void_p),
+        ("residual", c_void_p),
+        ("out", c_void_p),
+        ("so_n1", c_int64), ("so_n0", c_int64), ("so_y", c_int64), ("so_x", c_int64),
+        ("so_c1", c_int64), ("so_c0", c_int64),
+        ("ndiv", c_int32), ("cdiv", c_int32),
+        ("bn_force", c_int32),
+        ("stream", c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once). Raises if it has not been built (``__graft_entry__.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU/PyTorch fallback for the pfd_b200 kernels)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.pfd_version.restype = c_int32
+    lib.pfd_last_error.restype = c_char_p
+    lib.pfd_launch_count.restype = c_int64
+    lib.pfd_gemm_f16.argtypes = [POINTER(GemmDesc)]
+    lib.pfd_groupnorm_f16.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int64, c_int32,
+                                      c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.pfd_layernorm_f16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_float,
+                                      c_void_p, c_void_p]
+    lib.pfd_softmax_f16.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int64, c_float, c_void_p,
+                                    c_int32, c_void_p, c_int32, c_void_p]
+    lib.pfd_timestep_embedding_f16.argtypes = [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p]
+    lib.pfd_upsample2x_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.pfd_nchw_to_nhwc_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                         c_void_p, c_void_p]
+    lib.pfd_nhwc_to_nchw_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
+                                         c_float, c_float, c_float, c_void_p, c_void_p]
+    lib.pfd_im2col3x3_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_void_p, c_void_p]
+    lib.pfd_axpby_f16.argtypes = [c_void_p, c_float, c_void_p, c_float, c_int64, c_void_p, c_void_p]
+    lib.pfd_add_rowvec_f16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    lib.pfd_ddim_step_f16.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]
+    lib.pfd_window_gather_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                          c_void_p, c_void_p]
+    lib.pfd_window_scatter_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                           c_void_p, c_void_p, c_void_p]
+    lib.pfd_patch_merge_gather_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                               c_void_p]
+    if hasattr(lib, "pfd_flash_attn_f16"):
+        lib.pfd_flash_attn_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                           c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
+                                           c_int64, c_int64, c_int64, c_int32, c_void_p]
+    for name in EXPORTS:
+        if hasattr(lib, name) and name not in ("pfd_version", "pfd_last_error", "pfd_launch_count"):
+            getattr(lib, name).restype = c_int32
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pfd_last_error()
+        raise RuntimeError(f"{what} failed: {msg.decode() if msg else rc}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().pfd_launch_count())
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _chk16(t: torch.Tensor, name: str) -> None:
+    if t.dtype != torch.float16 or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA fp16 tensor, got {t.dtype} on {t.device}")
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM family
+# --------------------------------------------------------------------------------------------
+def gemm_raw(segs: Sequence[Tuple[torch.Tensor, int, int, Tuple[int, int, int]]], *, in_w: int,
+             in_h: int, stride: int, W: int, H: int, NB: int, w: torch.Tensor, N: int, K: int,
+             b_batch_stride: int = 0, alpha: float = 1.0, act: int = ACT_NONE,
+             bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None,
+             residual: Optional[torch.Tensor] = None, out: torch.Tensor,
+             so: Tuple[int, int, int, int, int, int], ndiv: int = 1, cdiv: int = 0,
+             bn_force: int = 0) -> None:
+    """Lowest-level call: ``segs`` is a list of (tensor, taps, channels, (sx, sy, sn))."""
+    d = GemmDesc()
+    d.nseg = len(segs)
+    for i, (t, taps, c, (sx, sy, sn)) in enumerate(segs):
+        _chk16(t, f"A[{i}]")
+        d.taps[i] = taps
+        d.a_c[i] = c
+        d.a_ptr[i] = t.data_ptr()
+        d.a_sx[i], d.a_sy[i], d.a_sn[i] = sx, sy, sn
+    d.in_w, d.in_h, d.stride = in_w, in_h, stride
+    d.W, d.H, d.NB = W, H, NB
+    _chk16(w, "B")
+    d.b_ptr = w.data_ptr()
+    d.N, d.K, d.b_batch_stride = N, K, b_batch_stride
+    d.alpha, d.act = alpha, act
+    d.bias = _p(bias)
+    d.rowadd = _p(rowadd)
+    d.residual = _p(residual)
+    d.out = out.data_ptr()
+    d.so_n1, d.so_n0, d.so_y, d.so_x, d.so_c1, d.so_c0 = so
+    d.ndiv, d.cdiv = ndiv, cdiv
+    d.bn_force = bn_force
+    d.stream = stream_ptr()
+    _check(load().pfd_gemm_f16(ctypes.byref(d)), "pfd_gemm_f16")
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           alpha: float = 1.0, x2: Optional[torch.Tensor] = None, bn_force: int = 0) -> torch.Tensor:
+    """out[M, N] = act(alpha * [x | x2] @ w^T + bias) + residual.  x: [M, K1] (row pitch = stride(0)),
+    optional x2: [M, K2]; w: [N, K1+K2] (GEGLU: tile-packed, output has N/2 columns)."""
+    M, K1 = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), device=x.device, dtype=torch.float16)
+    segs = [(x, 1, K1, (x.stride(0), x.stride(0) * M, x.stride(0) * M))]
+    if x2 is not None:
+        segs.append((x2, 1, x2.shape[1], (x2.stride(0), x2.stride(0) * M, x2.stride(0) * M)))
+    ldo = out.stride(0)
+    gemm_raw(segs, in_w=M, in_h=1, stride=1, W=M, H=1, NB=1, w=w, N=N, K=w.stride(0), alpha=alpha,
+             act=act, bias=bias, residual=residual, out=out, so=(0, 0, 0, ldo, 0, 1), bn_force=bn_force)
+    return out
+
+
+def geglu_tile(n2: int) -> int:
+    """N-tile width used for a GEGLU projection with 2*inner = n2 output features."""
+    for bn in (160, 256, 128, 192, 64):
+        if n2 % bn == 0:
+            return bn
+    raise RuntimeError(f"GEGLU width {n2} is not divisible by any supported N tile")
+
+
+def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor]):
+    """Re-order GEGLU.proj rows (attention.py:47-51: first half = value, second half = gate) so every
+    N tile holds [value(bn/2) | gate(bn/2)] for the same output columns. Returns (w, b, bn)."""
+    n2 = w.shape[0]
+    inner = n2 // 2
+    bn = geglu_tile(n2)
+    h = bn // 2
+    idx = torch.arange(n2, device=w.device).reshape(n2 // bn, 2, h)
+    tile = torch.arange(n2 // bn, device=w.device).reshape(-1, 1)
+    j = torch.arange(h, device=w.device).reshape(1, -1)
+    src = torch.stack([tile * h + j, inner + tile * h + j], dim=1).reshape(-1)
+    wp = w.index_select(0, src).contiguous()
+    bp = b.index_select(0, src).contiguous() if b is not None else None
+    return wp, bp, bn
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1,
+            rowadd: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            skip: Sequence[torch.Tensor] = ()) -> torch.Tensor:
+    """3x3 / pad 1 convolution on channel-last x [NB, H, W, C] with packed weights
+    w [Cout, 9*C (+ sum of skip channels)] (k = tap*C + c, then the 1x1 skip-segment channels).
+    ``skip`` tensors (same raster, stride 1 only) are extra 1x1 K-segments accumulated into the same
+    output — used to fuse ResBlock.skip_connection(x) (openaimodel.py:240,274) into out_layers' conv."""
+    NB, H, W, C = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((NB, Ho, Wo, N), device=x.device, dtype=torch.float16)
+    segs = [(x, 9, C, (x.stride(2), x.stride(1), x.stride(0)))]
+    for s in skip:
+        segs.append((s, 1, s.shape[3], (s.stride(2), s.stride(1), s.stride(0))))
+    gemm_raw(segs, in_w=W, in_h=H, stride=stride, W=Wo, H=Ho, NB=NB, w=w, N=N, K=w.stride(0), act=act,
+             bias=bias, rowadd=rowadd, residual=residual, out=out,
+             so=(out.stride(0), 0, out.stride(1), out.stride(2), 0, 1))
+    return out
+
+
+def conv1x1(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """1x1 conv on channel-last tensors == linear over flattened pixels."""
+    NB, H, W, C = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((NB, H, W, N), device=x.device, dtype=torch.float16)
+    r = residual.reshape(NB * H * W, -1) if residual is not None else None
+    linear(x.reshape(NB * H * W, C), w, bias, act=act, residual=r, out=out.reshape(NB * H * W, N),
+           x2=None if x2 is None else x2.reshape(NB * H * W, -1))
+    return out
+
+
+def bmm_nt(a: torch.Tensor, b: torch.Tensor, *, out: torch.Tensor, so, ndiv: int = 1, cdiv: int = 0,
+           alpha: float = 1.0) -> None:
+    """Batched out[b] = a[b] @ b[b]^T.  a: [B, M, K] contiguous-in-K, b: [B, N, K]; generic out strides."""
+    B, M, K = a.shape
+    N = b.shape[1]
+    gemm_raw([(a, 1, K, (a.stride(1), a.stride(1) * M, a.stride(0)))], in_w=M, in_h=1, stride=1, W=M,
+             H=1, NB=B, w=b, N=N, K=b.stride(1), b_batch_stride=b.stride(0), alpha=alpha, out=out,
+             so=so, ndiv=ndiv, cdiv=cdiv)
+
+
+# --------------------------------------------------------------------------------------------
+# normalisation / softmax / misc
+# --------------------------------------------------------------------------------------------
+_gn_ws = {}
+
+
+def _ws(device, nbytes: int) -> torch.Tensor:
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
+    t = _gn_ws.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 16), device=device, dtype=torch.uint8)
+        _gn_ws[key] = t
+    return t
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, silu: bool,
+              x2: Optional[torch.Tensor] = None, groups: int = 32,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over channel-last x [NB, H, W, C1] (optionally concatenated with x2 [.., C2])."""
+    NB, H, W, C1 = x.shape
+    C2 = x2.shape[3] if x2 is not None else 0
+    if out is None:
+        out = torch.empty((NB, H, W, C1 + C2), device=x.device, dtype=torch.float16)
+    ws = _ws(x.device, NB * groups * 16)
+    _check(load().pfd_groupnorm_f16(x.data_ptr(), C1, _p(x2), C2, NB, H * W, groups, gamma.data_ptr(),
+                                    beta.data_ptr(), eps, int(silu), out.data_ptr(), ws.data_ptr(),
+                                    stream_ptr()), "pfd_groupnorm_f16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *,
+              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    _check(load().pfd_layernorm_f16(x.data_ptr(), _p(residual), rows, C, gamma.data_ptr(), beta.data_ptr(),
+                                    eps, out.data_ptr(), stream_ptr()), "pfd_layernorm_f16")
+    return out
+
+
+def softmax_(s: torch.Tensor, scale: float, *, bias: Optional[torch.Tensor] = None, nheads: int = 1,
+             mask: Optional[torch.Tensor] = None, nwin: int = 1) -> torch.Tensor:
+    """In-place row softmax over s [batch, rows, cols] (see pfd_softmax_f16)."""
+    batch, rows, cols = s.shape
+    _check(load().pfd_softmax_f16(s.data_ptr(), batch, rows, cols, s.stride(1), scale, _p(bias), nheads,
+                                  _p(mask), nwin, stream_ptr()), "pfd_softmax_f16")
+    return s
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float16)
+    _check(load().pfd_timestep_embedding_f16(t.data_ptr(), t.shape[0], dim, max_period, out.data_ptr(),
+                                             stream_ptr()), "pfd_timestep_embedding_f16")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    NB, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((NB, 2 * H, 2 * W, C), device=x.device, dtype=torch.float16)
+    _check(load().pfd_upsample2x_f16(x.data_ptr(), NB, H, W, C, out.data_ptr(), stream_ptr()),
+           "pfd_upsample2x_f16")
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, cpad: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    NB, C, H, W = x.shape
+    cpad = cpad or C
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((NB, H, W, cpad), device=x.device, dtype=torch.float16)
+    if x.dtype not in (torch.float16, torch.float32):
+        raise RuntimeError(f"nchw_to_nhwc: unsupported dtype {x.dtype}")
+    _check(load().pfd_nchw_to_nhwc_f16(x.data_ptr(), int(x.dtype == torch.float32), NB, C, H, W, cpad,
+                                       out.data_ptr(), stream_ptr()), "pfd_nchw_to_nhwc_f16")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, C: Optional[int] = None, *, mul: float = 1.0, add: float = 0.0,
+                 lo: float = -65504.0, hi: float = 65504.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    NB, H, W, Cpad = x.shape
+    C = C or Cpad
+    if out is None:
+        out = torch.empty((NB, C, H, W), device=x.device, dtype=torch.float16)
+    _check(load().pfd_nhwc_to_nchw_f16(x.data_ptr(), NB, C, H, W, Cpad, mul, add, lo, hi, out.data_ptr(),
+                                       stream_ptr()), "pfd_nhwc_to_nchw_f16")
+    return out
+
+
+def im2col3x3(x: torch.Tensor, kpad: int, stride: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    NB, H, W, C = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty((NB, Ho, Wo, kpad), device=x.device, dtype=torch.float16)
+    _check(load().pfd_im2col3x3_f16(x.data_ptr(), NB, H, W, C, stride, kpad, out.data_ptr(), stream_ptr()),
+           "pfd_im2col3x3_f16")
+    return out
+
+
+def axpby(a: torch.Tensor, sa: float, b: Optional[torch.Tensor] = None, sb: float = 0.0,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(a)
+    _check(load().pfd_axpby_f16(a.data_ptr(), sa, _p(b), sb, a.numel(), out.data_ptr(), stream_ptr()),
+           "pfd_axpby_f16")
+    return out
+
+
+def add_rowvec(a: torch.Tensor, row: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    C = a.shape[-1]
+    if out is None:
+        out = torch.empty_like(a)
+    _check(load().pfd_add_rowvec_f16(a.data_ptr(), row.data_ptr(), a.numel() // C, C, out.data_ptr(),
+                                     stream_ptr()), "pfd_add_rowvec_f16")
+    return out
+
+
+def ddim_step(eps: torch.Tensor, x: torch.Tensor, guidance: float, coef: torch.Tensor,
+              step: Optional[torch.Tensor], x_prev: torch.Tensor, pred_x0: Optional[torch.Tensor]) -> None:
+    _check(load().pfd_ddim_step_f16(eps.data_ptr(), x.data_ptr(), x.numel(), guidance, coef.data_ptr(),
+                                    _p(step), x_prev.data_ptr(), _p(pred_x0), stream_ptr()),
+           "pfd_ddim_step_f16")
+
+
+def window_gather(x: torch.Tensor, ws: int, shift: int) -> torch.Tensor:
+    B, H, W, C = x.shape
+    Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+    out = torch.empty((B * (Hp // ws) * (Wp // ws), ws * ws, C), device=x.device, dtype=torch.float16)
+    _check(load().pfd_window_gather_f16(x.data_ptr(), B, H, W, C, ws, shift, out.data_ptr(), stream_ptr()),
+           "pfd_window_gather_f16")
+    return out
+
+
+def window_scatter(win: torch.Tensor, B: int, H: int, W: int, ws: int, shift: int,
+                   residual: Optional[torch.Tensor]) -> torch.Tensor:
+    C = win.shape[-1]
+    out = torch.empty((B, H, W, C), device=win.device, dtype=torch.float16)
+    _check(load().pfd_window_scatter_f16(win.data_ptr(), B, H, W, C, ws, shift, _p(residual),
+                                         out.data_ptr(), stream_ptr()), "pfd_window_scatter_f16")
+    return out
+
+
+def patch_merge_gather(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, C = x.shape
+    out = torch.empty((B, (H + 1) // 2, (W + 1) // 2, 4 * C), device=x.device, dtype=torch.float16)
+    _check(load().pfd_patch_merge_gather_f16(x.data_ptr(), B, H, W, C, out.data_ptr(), stream_ptr()),
+           "pfd_patch_merge_gather_f16")
+    return out

@@ -1,0 +1,259 @@
+"""GPU parity tests of the C-ABI kernels against plain torch fp32 math on the same fp16 inputs.
+
+Every call goes through ctypes -> libpfd_b200.so (pfd_b200/native.py); torch is only the checker.
+Tolerances: outputs are fp16, accumulation fp32 -> |err| <= 2^-9 * |ref| + small abs term.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nv():
+    from pfd_b200 import native
+    native.load()
+    return native
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to("cuda", torch.float16)
+
+
+def close(out, ref, rtol=4e-3, atol=4e-3):
+    out = out.float()
+    ref = ref.float()
+    err = (out - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{bad}/{err.numel()} mismatches, max err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 320, 320), (4096, 320, 320), (1000, 1280, 768),
+                                   (77, 640, 1280), (512, 24, 40), (300, 2560, 320), (8, 1280, 1280)])
+def test_linear(nv, M, N, K):
+    x = rnd(M, K, scale=1.0)
+    w = rnd(N, K, scale=K ** -0.5, seed=1)
+    b = rnd(N, seed=2)
+    out = nv.linear(x, w, b)
+    torch.cuda.synchronize()
+    close(out, x.float() @ w.float().t() + b.float())
+
+
+@pytest.mark.parametrize("act", ["silu", "gelu", "relu"])
+def test_linear_act_residual(nv, act):
+    M, N, K = 640, 384, 192
+    x, w, b, r = rnd(M, K), rnd(N, K, scale=K ** -0.5, seed=1), rnd(N, seed=2), rnd(M, N, seed=3)
+    code = {"silu": nv.ACT_SILU, "gelu": nv.ACT_GELU, "relu": nv.ACT_RELU}[act]
+    out = nv.linear(x, w, b, act=code, residual=r)
+    torch.cuda.synchronize()
+    y = x.float() @ w.float().t() + b.float()
+    y = {"silu": F.silu, "gelu": F.gelu, "relu": F.relu}[act](y) + r.float()
+    close(out, y)
+
+
+def test_linear_two_segments(nv):
+    M, N, K1, K2 = 512, 320, 640, 320
+    x1, x2 = rnd(M, K1), rnd(M, K2, seed=5)
+    w = rnd(N, K1 + K2, scale=(K1 + K2) ** -0.5, seed=1)
+    out = nv.linear(x1, w, None, x2=x2)
+    torch.cuda.synchronize()
+    close(out, torch.cat([x1, x2], 1).float() @ w.float().t())
+
+
+@pytest.mark.parametrize("C", [64, 320])
+def test_geglu(nv, C):
+    M, inner = 512, 4 * C
+    x = rnd(M, C)
+    w = rnd(2 * inner, C, scale=C ** -0.5, seed=1)
+    b = rnd(2 * inner, seed=2)
+    wp, bp, bn = nv.pack_geglu(w, b)
+    out = nv.linear(x, wp, bp, act=nv.ACT_GEGLU, bn_force=bn)
+    torch.cuda.synchronize()
+    y = (x.float() @ w.float().t() + b.float()).half()
+    v, g = y.chunk(2, dim=-1)
+    close(out, v.float() * F.gelu(g.float()), rtol=8e-3, atol=8e-3)
+
+
+@pytest.mark.parametrize("NB,H,W,C,N", [(2, 64, 64, 320, 320), (3, 8, 8, 128, 64), (2, 32, 32, 640, 320),
+                                        (1, 16, 16, 1280, 640), (2, 24, 24, 64, 128), (1, 12, 12, 64, 64),
+                                        (1, 128, 128, 128, 128)])
+def test_conv3x3(nv, NB, H, W, C, N):
+    x = rnd(NB, H, W, C)
+    w = rnd(N, C, 3, 3, scale=(9 * C) ** -0.5, seed=1)
+    b = rnd(N, seed=2)
+    emb = rnd(NB, N, seed=3)
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = nv.conv3x3(x, wp, b, rowadd=emb)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1) + emb.float()[:, :, None, None]
+    close(out, ref.permute(0, 2, 3, 1))
+
+
+def test_conv3x3_fused_skip(nv):
+    NB, H, W, C, Cx1, Cx2, N = 2, 32, 32, 320, 640, 320, 320
+    h, x1, x2 = rnd(NB, H, W, C), rnd(NB, H, W, Cx1, seed=4), rnd(NB, H, W, Cx2, seed=5)
+    w = rnd(N, C, 3, 3, scale=(9 * C) ** -0.5, seed=1)
+    ws = rnd(N, Cx1 + Cx2, scale=(Cx1 + Cx2) ** -0.5, seed=6)
+    b = rnd(N, seed=2)
+    wp = torch.cat([w.permute(0, 2, 3, 1).reshape(N, 9 * C), ws], dim=1).contiguous()
+    out = nv.conv3x3(h, wp, b, skip=[x1, x2])
+    torch.cuda.synchronize()
+    ref = F.conv2d(h.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1)
+    ref = ref + F.conv2d(torch.cat([x1, x2], 3).float().permute(0, 3, 1, 2), ws.float()[:, :, None, None])
+    close(out, ref.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("NB,H,W,C,N", [(2, 64, 64, 320, 320), (1, 32, 32, 64, 64), (2, 16, 16, 128, 128)])
+def test_conv3x3_stride2(nv, NB, H, W, C, N):
+    x = rnd(NB, H, W, C)
+    w = rnd(N, C, 3, 3, scale=(9 * C) ** -0.5, seed=1)
+    b = rnd(N, seed=2)
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = nv.conv3x3(x, wp, b, stride=2)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1, stride=2)
+    close(out, ref.permute(0, 2, 3, 1))
+
+
+def test_bmm_nt_headsplit(nv):
+    # QK^T per (batch, head): a [B*h, M, d], b [B*h, Nk, d] -> s [B*h, M, Nk]
+    BH, M, Nk, d = 16, 256, 148 + 4, 40
+    a, b = rnd(BH, M, d), rnd(BH, Nk, d, seed=1)
+    s = torch.empty(BH, M, Nk, device="cuda", dtype=torch.float16)
+    nv.bmm_nt(a, b, out=s, so=(M * Nk, 0, 0, Nk, 0, 1))
+    torch.cuda.synchronize()
+    close(s, torch.bmm(a.float(), b.float().transpose(1, 2)))
+
+
+@pytest.mark.parametrize("C1,C2,HW,silu", [(320, 0, 4096, True), (1280, 640, 256, True), (640, 0, 1024, False),
+                                           (128, 0, 65536, True), (64, 64, 64, True)])
+def test_groupnorm(nv, C1, C2, HW, silu):
+    NB = 2
+    side = int(math.isqrt(HW))
+    x1 = rnd(NB, side, side, C1, scale=2.0) + 0.5
+    x2 = rnd(NB, side, side, C2, seed=3) if C2 else None
+    C = C1 + C2
+    gamma, beta = rnd(C, seed=4) + 1.0, rnd(C, seed=5)
+    out = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)
+    torch.cuda.synchronize()
+    xc = x1 if x2 is None else torch.cat([x1, x2], 3)
+    ref = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    close(out, ref.permute(0, 2, 3, 1), rtol=6e-3, atol=6e-3)
+
+
+@pytest.mark.parametrize("C", [192, 320, 768, 1280, 1536])
+def test_layernorm(nv, C):
+    x = rnd(1000, C, scale=2.0) + 0.3
+    r = rnd(1000, C, seed=9)
+    g, b = rnd(C, seed=4) + 1.0, rnd(C, seed=5)
+    out = nv.layernorm(x, g, b, 1e-5)
+    out2 = nv.layernorm(x, g, b, 1e-5, residual=r)
+    torch.cuda.synchronize()
+    close(out, F.layer_norm(x.float(), (C,), g.float(), b.float(), 1e-5), rtol=6e-3, atol=6e-3)
+    close(out2, F.layer_norm((x + r).float(), (C,), g.float(), b.float(), 1e-5), rtol=6e-3, atol=6e-3)
+
+
+def test_softmax_plain_and_bias(nv):
+    B, R, Cc = 12, 144, 144
+    s = rnd(B, R, Cc, scale=3.0)
+    ref = torch.softmax((s.float() * 0.125).half().float(), -1)
+    out = nv.softmax_(s.clone(), 0.125)
+    nheads, nwin = 3, 4
+    bias, mask = rnd(nheads, R, Cc, seed=2), rnd(nwin, R, Cc, seed=3)
+    out2 = nv.softmax_(s.clone(), 0.125, bias=bias, nheads=nheads, mask=mask, nwin=nwin)
+    torch.cuda.synchronize()
+    close(out, ref, rtol=4e-3, atol=1e-4)
+    b_idx = torch.arange(B, device="cuda")
+    t = (s.float() * 0.125).half()
+    t = (t + bias[b_idx % nheads]).half()
+    t = (t + mask[(b_idx // nheads) % nwin]).half()
+    close(out2, torch.softmax(t.float(), -1), rtol=4e-3, atol=1e-4)
+
+
+def test_softmax_long_rows(nv):
+    s = rnd(2, 64, 4096, scale=4.0)
+    out = nv.softmax_(s.clone(), 512 ** -0.5)
+    torch.cuda.synchronize()
+    close(out, torch.softmax((s.float() * 512 ** -0.5).half().float(), -1), rtol=4e-3, atol=1e-5)
+
+
+def test_timestep_embedding(nv):
+    t = torch.tensor([1, 21, 501, 981], device="cuda", dtype=torch.int64)
+    out = nv.timestep_embedding(t, 320)
+    torch.cuda.synchronize()
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device="cuda") / half)
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    close(out, ref, rtol=2e-3, atol=2e-3)
+
+
+def test_layout_and_resample(nv):
+    x = rnd(2, 8, 6, 10)  # NCHW
+    nhwc = nv.nchw_to_nhwc(x, cpad=16)
+    back = nv.nhwc_to_nchw(nhwc, 8, mul=0.5, add=0.5, lo=0.0, hi=1.0)
+    x32 = x.float()
+    nhwc32 = nv.nchw_to_nhwc(x32)
+    y = rnd(2, 5, 7, 64)
+    up = nv.upsample2x(y)
+    col = nv.im2col3x3(rnd(2, 6, 6, 4, seed=8), 40)
+    torch.cuda.synchronize()
+    assert torch.equal(nhwc[..., :8], x.permute(0, 2, 3, 1)) and nhwc[..., 8:].abs().sum() == 0
+    assert torch.equal(nhwc32, x.permute(0, 2, 3, 1))
+    close(back, (x.float() * 0.5 + 0.5).half().float().clamp(0, 1), rtol=1e-3, atol=1e-3)
+    ref_up = F.interpolate(y.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref_up)
+    xs = rnd(2, 6, 6, 4, seed=8)
+    unf = F.unfold(xs.permute(0, 3, 1, 2).float(), 3, padding=1)  # [N, C*9, L] ordered (c, tap)
+    unf = unf.reshape(2, 4, 9, 36).permute(0, 3, 2, 1).reshape(2, 6, 6, 36)
+    assert torch.equal(col[..., :36].float(), unf) and col[..., 36:].abs().sum() == 0
+
+
+def test_window_roundtrip_and_patch_merge(nv):
+    B, H, W, C, ws, shift = 2, 16, 20, 64, 12, 6
+    x = rnd(B, H, W, C)
+    win = nv.window_gather(x, ws, shift)
+    res = rnd(B, H, W, C, seed=3)
+    back = nv.window_scatter(win, B, H, W, ws, shift, res)
+    pm = nv.patch_merge_gather(rnd(1, 5, 7, 64, seed=4))
+    torch.cuda.synchronize()
+    # reference via torch ops (swin.py:269-287)
+    Hp, Wp = 24, 24
+    xp = F.pad(x.float(), (0, 0, 0, Wp - W, 0, Hp - H))
+    xs = torch.roll(xp, shifts=(-shift, -shift), dims=(1, 2))
+    ref = xs.view(B, Hp // ws, ws, Wp // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, C)
+    assert torch.equal(win.float(), ref)
+    close(back, x.float() + res.float(), rtol=1e-3, atol=1e-3)
+    y = rnd(1, 5, 7, 64, seed=4).float()
+    yp = F.pad(y, (0, 0, 0, 1, 0, 1))
+    refpm = torch.cat([yp[:, 0::2, 0::2], yp[:, 1::2, 0::2], yp[:, 0::2, 1::2], yp[:, 1::2, 1::2]], -1)
+    assert torch.equal(pm.float(), refpm)
+
+
+def test_ddim_step_matches_fp16_eager(nv):
+    B = 2
+    eps = rnd(2 * B, 4, 16, 16)
+    x = rnd(B, 4, 16, 16, seed=1)
+    coef = torch.tensor([[0.5, 0.7, 0.0, math.sqrt(0.5)], [0.9, 0.95, 0.0, math.sqrt(0.1)]],
+                        device="cuda", dtype=torch.float32)
+    step = torch.tensor([1], device="cuda", dtype=torch.int32)
+    xp, p0 = torch.empty_like(x), torch.empty_like(x)
+    nv.ddim_step(eps, x, 2.0, coef, step, xp, p0)
+    torch.cuda.synchronize()
+    e_u, e_c = eps.chunk(2)
+    e = e_u + 2.0 * (e_c - e_u)
+    a_t = torch.full((B, 1, 1, 1), 0.9, device="cuda", dtype=torch.float16)
+    a_p = torch.full((B, 1, 1, 1), 0.95, device="cuda", dtype=torch.float16)
+    sg = torch.full((B, 1, 1, 1), 0.0, device="cuda", dtype=torch.float16)
+    s1 = torch.full((B, 1, 1, 1), math.sqrt(0.1), device="cuda", dtype=torch.float16)
+    pred = (x - s1 * e) / a_t.sqrt()
+    ref = a_p.sqrt() * pred + (1. - a_p - sg ** 2).sqrt() * e
+    close(p0, pred, rtol=2e-3, atol=2e-3)
+    close(xp, ref, rtol=2e-3, atol=2e-3)
