@@ -25,6 +25,11 @@ extern "C" {
 #endif
 
 #define PFD_ABI_VERSION 1
+#if defined(__GNUC__)
+#define PFD_API __attribute__((visibility("default")))
+#else
+#define PFD_API
+#endif
 #define PFD_MAX_SEG 3
 
 /* activation codes for pfd_gemm_desc.act */
@@ -36,10 +41,10 @@ enum {
   PFD_ACT_GEGLU = 4   /* value*gelu(gate), weights packed [value|gate] per N tile (attention.py:44-51) */
 };
 
-int pfd_version(void);
-const char* pfd_last_error(void);
+PFD_API int pfd_version(void);
+PFD_API const char* pfd_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py: gpu_launches) */
-int64_t pfd_launch_count(void);
+PFD_API int64_t pfd_launch_count(void);
 
 /*
  * pfd_gemm_f16 — the tcgen05 tensor-core contraction used for every Linear, 1x1 conv, 3x3 conv
@@ -93,7 +98,7 @@ typedef struct pfd_gemm_desc {
   void* stream;
 } pfd_gemm_desc;
 
-int pfd_gemm_f16(const pfd_gemm_desc* d);
+PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d);
 
 /*
  * GroupNorm(32 groups) [+ SiLU] over channel-last fp16, optionally over the channel-concatenation
@@ -104,13 +109,13 @@ int pfd_gemm_f16(const pfd_gemm_desc* d);
  * ws: scratch of at least NB*groups*16 bytes (fp64 sum / sum-of-squares per (image, group)),
  *     16-byte aligned; zeroed by the call.
  */
-int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, int32_t NB,
+PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, int32_t NB,
                       int64_t HW, int32_t groups, const void* gamma, const void* beta, float eps,
                       int32_t silu, void* out, float* ws, void* stream);
 
 /* LayerNorm over the last dim of [rows, C] fp16 (attention.py:294-296, swin.py norms, seecoder.py norms).
  * Optional fused residual: out = LN(x + res) (post-norm layers of seecoder.py:85-90,135-136). */
-int pfd_layernorm_f16(const void* x, const void* res, int64_t rows, int32_t C, const void* gamma,
+PFD_API int pfd_layernorm_f16(const void* x, const void* res, int64_t rows, int32_t C, const void* gamma,
                       const void* beta, float eps, void* out, void* stream);
 
 /*
@@ -120,34 +125,34 @@ int pfd_layernorm_f16(const void* x, const void* res, int64_t rows, int32_t C, c
  * swin.py:187-203).  bias: [nheads, rows, cols] fp16 or NULL, selected by (b % nheads);
  * mask: [nwin, rows, cols] fp16 or NULL, selected by ((b / nheads) % nwin).
  */
-int pfd_softmax_f16(void* s, int64_t batch, int32_t rows, int32_t cols, int64_t ld, float scale,
+PFD_API int pfd_softmax_f16(void* s, int64_t batch, int32_t rows, int32_t cols, int64_t ld, float scale,
                     const void* bias, int32_t nheads, const void* mask, int32_t nwin, void* stream);
 
 /* sinusoidal timestep embedding [cos | sin], fp32 math, fp16 out (diffusion_utils.py:131-151). */
-int pfd_timestep_embedding_f16(const int64_t* t, int32_t n, int32_t dim, float max_period,
+PFD_API int pfd_timestep_embedding_f16(const int64_t* t, int32_t n, int32_t dim, float max_period,
                                void* out, void* stream);
 
 /* nearest-neighbour 2x upsample, channel-last (openaimodel.py:114, autokl_modules.py:54). */
-int pfd_upsample2x_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, void* out,
+PFD_API int pfd_upsample2x_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, void* out,
                        void* stream);
 
 /* layout converts at the pipeline edges: NCHW fp16/fp32 <-> channel-last fp16 (with channel pad). */
-int pfd_nchw_to_nhwc_f16(const void* x, int32_t src_is_f32, int32_t NB, int32_t C, int32_t H,
+PFD_API int pfd_nchw_to_nhwc_f16(const void* x, int32_t src_is_f32, int32_t NB, int32_t C, int32_t H,
                          int32_t W, int32_t Cpad, void* out, void* stream);
 /* out_nchw[n,c,y,x] = clamp(x[n,y,x,c]*mul + add, lo, hi) for c < C (autokl.py:47,53: (dec+1)/2, clamp) */
-int pfd_nhwc_to_nchw_f16(const void* x, int32_t NB, int32_t C, int32_t H, int32_t W, int32_t Cpad,
+PFD_API int pfd_nhwc_to_nchw_f16(const void* x, int32_t NB, int32_t C, int32_t H, int32_t W, int32_t Cpad,
                          float mul, float add, float lo, float hi, void* out, void* stream);
 
 /* explicit im2col for 3x3 convs whose Cin is too small for the TMA path (Cin<8: UNet/VAE conv_in,
  * ControlNet hint stem): out[n,y,x, tap*Cin + c] (K padded to Kpad with zeros). */
-int pfd_im2col3x3_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, int32_t stride,
+PFD_API int pfd_im2col3x3_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, int32_t stride,
                       int32_t Kpad, void* out, void* stream);
 
 /* out = a*sa + b*sb (elementwise fp16, fp32 math); b may be NULL. */
-int pfd_axpby_f16(const void* a, float sa, const void* b, float sb, int64_t n, void* out,
+PFD_API int pfd_axpby_f16(const void* a, float sa, const void* b, float sb, int64_t n, void* out,
                   void* stream);
 /* out[n, :] = a[n, :] + row[:]  (level/position embeddings, seecoder.py:402,513) */
-int pfd_add_rowvec_f16(const void* a, const void* row, int64_t rows, int32_t C, void* out,
+PFD_API int pfd_add_rowvec_f16(const void* a, const void* row, int64_t rows, int32_t C, void* out,
                        void* stream);
 
 /*
@@ -159,19 +164,19 @@ int pfd_add_rowvec_f16(const void* a, const void* row, int64_t rows, int32_t C, 
  * device table coef[step*4 + {0..3}] = {a_t, a_prev, sigma_t, sqrt_one_minus_at} (fp32) indexed by
  * the device-side int *step so that a captured CUDA graph can be replayed for every step.
  */
-int pfd_ddim_step_f16(const void* eps, const void* x, int64_t half_n, float guidance,
+PFD_API int pfd_ddim_step_f16(const void* eps, const void* x, int64_t half_n, float guidance,
                       const float* coef, const int32_t* step, void* x_prev, void* pred_x0,
                       void* stream);
 
 /* Swin window plumbing on channel-last [B,H,W,C] (swin.py:269-304): pad + cyclic shift + window
  * partition in one gather (fwd) and the inverse scatter + crop (bwd). */
-int pfd_window_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ws,
+PFD_API int pfd_window_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ws,
                           int32_t shift, void* out, void* stream);
-int pfd_window_scatter_f16(const void* win, int32_t B, int32_t H, int32_t W, int32_t C,
+PFD_API int pfd_window_scatter_f16(const void* win, int32_t B, int32_t H, int32_t W, int32_t C,
                            int32_t ws, int32_t shift, const void* residual, void* out,
                            void* stream);
 /* PatchMerging 2x2 gather -> [B, H/2*W/2, 4C] in the reference's x0,x1,x2,x3 order (swin.py:341-346). */
-int pfd_patch_merge_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C,
+PFD_API int pfd_patch_merge_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C,
                                void* out, void* stream);
 
 #ifdef __cplusplus

@@ -19,6 +19,6 @@ int set_error(const char* fmt, ...) {
 }
 }  // namespace pfd
 
-extern "C" int pfd_version(void) { return PFD_ABI_VERSION; }
-extern "C" const char* pfd_last_error(void) { return pfd::g_last_error.c_str(); }
-extern "C" int64_t pfd_launch_count(void) { return pfd::g_launches.load(); }
+extern "C" PFD_API int pfd_version(void) { return PFD_ABI_VERSION; }
+extern "C" PFD_API const char* pfd_last_error(void) { return pfd::g_last_error.c_str(); }
+extern "C" PFD_API int64_t pfd_launch_count(void) { return pfd::g_launches.load(); }

@@ -521,7 +521,7 @@ static inline int grid_for(long long total, int threads) {
 
 using namespace pfd;
 
-extern "C" int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, int32_t NB,
+extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, int32_t NB,
                                  int64_t HW, int32_t groups, const void* gamma, const void* beta,
                                  float eps, int32_t silu, void* out, float* ws, void* stream) {
   const int C = c1 + (x2 ? c2 : 0);
@@ -549,7 +549,7 @@ extern "C" int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int
   return check_launch("gn_apply");
 }
 
-extern "C" int pfd_layernorm_f16(const void* x, const void* res, int64_t rows, int32_t C,
+extern "C" PFD_API int pfd_layernorm_f16(const void* x, const void* res, int64_t rows, int32_t C,
                                  const void* gamma, const void* beta, float eps, void* out,
                                  void* stream) {
   if (C % 8 || C > 8 * 32 * 8) return set_error("pfd_layernorm_f16: C=%d unsupported", C);
@@ -569,7 +569,7 @@ extern "C" int pfd_layernorm_f16(const void* x, const void* res, int64_t rows, i
   return check_launch("layernorm");
 }
 
-extern "C" int pfd_softmax_f16(void* s, int64_t batch, int32_t rows, int32_t cols, int64_t ld,
+extern "C" PFD_API int pfd_softmax_f16(void* s, int64_t batch, int32_t rows, int32_t cols, int64_t ld,
                                float scale, const void* bias, int32_t nheads, const void* mask,
                                int32_t nwin, void* stream) {
   if (cols <= 0 || cols > 12288) return set_error("pfd_softmax_f16: cols=%d unsupported", cols);
@@ -589,7 +589,7 @@ extern "C" int pfd_softmax_f16(void* s, int64_t batch, int32_t rows, int32_t col
   return check_launch("softmax");
 }
 
-extern "C" int pfd_timestep_embedding_f16(const int64_t* t, int32_t n, int32_t dim, float max_period,
+extern "C" PFD_API int pfd_timestep_embedding_f16(const int64_t* t, int32_t n, int32_t dim, float max_period,
                                           void* out, void* stream) {
   const int total = n * (dim / 2);
   timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -597,7 +597,7 @@ extern "C" int pfd_timestep_embedding_f16(const int64_t* t, int32_t n, int32_t d
   return check_launch("timestep_embedding");
 }
 
-extern "C" int pfd_upsample2x_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, void* out,
+extern "C" PFD_API int pfd_upsample2x_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, void* out,
                                   void* stream) {
   if (C % 8) return set_error("pfd_upsample2x_f16: C=%d", C);
   const long long total = (long long)NB * 4 * H * W * (C / 8);
@@ -606,7 +606,7 @@ extern "C" int pfd_upsample2x_f16(const void* x, int32_t NB, int32_t H, int32_t 
   return check_launch("upsample2x");
 }
 
-extern "C" int pfd_nchw_to_nhwc_f16(const void* x, int32_t src_is_f32, int32_t NB, int32_t C, int32_t H,
+extern "C" PFD_API int pfd_nchw_to_nhwc_f16(const void* x, int32_t src_is_f32, int32_t NB, int32_t C, int32_t H,
                                     int32_t W, int32_t Cpad, void* out, void* stream) {
   const long long total = (long long)NB * H * W * Cpad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -617,7 +617,7 @@ extern "C" int pfd_nchw_to_nhwc_f16(const void* x, int32_t src_is_f32, int32_t N
   return check_launch("nchw_to_nhwc");
 }
 
-extern "C" int pfd_nhwc_to_nchw_f16(const void* x, int32_t NB, int32_t C, int32_t H, int32_t W, int32_t Cpad,
+extern "C" PFD_API int pfd_nhwc_to_nchw_f16(const void* x, int32_t NB, int32_t C, int32_t H, int32_t W, int32_t Cpad,
                                     float mul, float add, float lo, float hi, void* out, void* stream) {
   const long long total = (long long)NB * C * H * W;
   nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -625,7 +625,7 @@ extern "C" int pfd_nhwc_to_nchw_f16(const void* x, int32_t NB, int32_t C, int32_
   return check_launch("nhwc_to_nchw");
 }
 
-extern "C" int pfd_im2col3x3_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, int32_t stride,
+extern "C" PFD_API int pfd_im2col3x3_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, int32_t stride,
                                  int32_t Kpad, void* out, void* stream) {
   if (Kpad < 9 * C || Kpad % 8) return set_error("pfd_im2col3x3_f16: Kpad=%d for C=%d", Kpad, C);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
@@ -635,14 +635,14 @@ extern "C" int pfd_im2col3x3_f16(const void* x, int32_t NB, int32_t H, int32_t W
   return check_launch("im2col3x3");
 }
 
-extern "C" int pfd_axpby_f16(const void* a, float sa, const void* b, float sb, int64_t n, void* out,
+extern "C" PFD_API int pfd_axpby_f16(const void* a, float sa, const void* b, float sb, int64_t n, void* out,
                              void* stream) {
   axpby_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(a), sa, static_cast<const __half*>(b), sb, n, static_cast<__half*>(out));
   return check_launch("axpby");
 }
 
-extern "C" int pfd_add_rowvec_f16(const void* a, const void* row, int64_t rows, int32_t C, void* out,
+extern "C" PFD_API int pfd_add_rowvec_f16(const void* a, const void* row, int64_t rows, int32_t C, void* out,
                                   void* stream) {
   if (C % 8) return set_error("pfd_add_rowvec_f16: C=%d", C);
   add_rowvec_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -650,7 +650,7 @@ extern "C" int pfd_add_rowvec_f16(const void* a, const void* row, int64_t rows, 
   return check_launch("add_rowvec");
 }
 
-extern "C" int pfd_ddim_step_f16(const void* eps, const void* x, int64_t half_n, float guidance,
+extern "C" PFD_API int pfd_ddim_step_f16(const void* eps, const void* x, int64_t half_n, float guidance,
                                  const float* coef, const int32_t* step, void* x_prev, void* pred_x0,
                                  void* stream) {
   ddim_step_kernel<<<grid_for(half_n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -659,7 +659,7 @@ extern "C" int pfd_ddim_step_f16(const void* eps, const void* x, int64_t half_n,
   return check_launch("ddim_step");
 }
 
-extern "C" int pfd_window_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ws,
+extern "C" PFD_API int pfd_window_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ws,
                                      int32_t shift, void* out, void* stream) {
   if (C % 8) return set_error("pfd_window_gather_f16: C=%d", C);
   const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
@@ -669,7 +669,7 @@ extern "C" int pfd_window_gather_f16(const void* x, int32_t B, int32_t H, int32_
   return check_launch("window_gather");
 }
 
-extern "C" int pfd_window_scatter_f16(const void* win, int32_t B, int32_t H, int32_t W, int32_t C,
+extern "C" PFD_API int pfd_window_scatter_f16(const void* win, int32_t B, int32_t H, int32_t W, int32_t C,
                                       int32_t ws, int32_t shift, const void* residual, void* out,
                                       void* stream) {
   if (C % 8) return set_error("pfd_window_scatter_f16: C=%d", C);
@@ -681,7 +681,7 @@ extern "C" int pfd_window_scatter_f16(const void* win, int32_t B, int32_t H, int
   return check_launch("window_scatter");
 }
 
-extern "C" int pfd_patch_merge_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C,
+extern "C" PFD_API int pfd_patch_merge_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C,
                                           void* out, void* stream) {
   if (C % 8) return set_error("pfd_patch_merge_gather_f16: C=%d", C);
   const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * 4 * (C / 8);

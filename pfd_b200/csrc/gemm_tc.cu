@@ -388,7 +388,7 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
 
 using namespace pfd;
 
-extern "C" int pfd_gemm_f16(const pfd_gemm_desc* d) {
+extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   if (!d) return set_error("pfd_gemm_f16: null descriptor");
   if (d->nseg < 1 || d->nseg > PFD_MAX_SEG) return set_error("pfd_gemm_f16: nseg %d out of range", d->nseg);
   if (d->N <= 0 || d->N % 8) return set_error("pfd_gemm_f16: N=%d must be a positive multiple of 8", d->N);

@@ -26,7 +26,7 @@ EXPORTS = [
     "pfd_layernorm_f16", "pfd_softmax_f16", "pfd_timestep_embedding_f16", "pfd_upsample2x_f16",
     "pfd_nchw_to_nhwc_f16", "pfd_nhwc_to_nchw_f16", "pfd_im2col3x3_f16", "pfd_axpby_f16",
     "pfd_add_rowvec_f16", "pfd_ddim_step_f16", "pfd_window_gather_f16", "pfd_window_scatter_f16",
-    "pfd_patch_merge_gather_f16", "pfd_flash_attn_f16",
+    "pfd_patch_merge_gather_f16",
 ]
 
 

@@ -1,0 +1,109 @@
+"""Import harness for the UNMODIFIED reference (SHI-Labs/Prompt-Free-Diffusion at /root/reference).
+
+Only usable in the build container (the reference tree does not travel to the GPU box); used by
+tools/make_golden.py and tools/validate_oracle.py to pin the oracle.  Recipe: SURVEY.md App. D.
+Nothing here is imported by the product or by the tests.
+"""
+import os
+import sys
+import types
+
+REF = os.environ.get("PFD_REFERENCE", "/root/reference")
+
+
+class EasyDict(dict):
+    """Minimal attr-dict stand-in for the `easydict` package (lib/cfg_helper.py:13)."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        d = dict(d or {}, **kw)
+        for k, v in d.items():
+            self[k] = v
+
+    @classmethod
+    def _wrap(cls, v):
+        if isinstance(v, dict) and not isinstance(v, EasyDict):
+            return cls(v)
+        if isinstance(v, (list, tuple)):
+            return type(v)(cls._wrap(x) for x in v)
+        return v
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, self._wrap(v))
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def update(self, *a, **kw):
+        for k, v in dict(*a, **kw).items():
+            self[k] = v
+
+    def __deepcopy__(self, memo):
+        import copy
+        return EasyDict({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+
+def install_shims():
+    sys.modules.setdefault("easydict", types.SimpleNamespace(EasyDict=EasyDict))
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        mpl.__path__ = []
+        plt = types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt
+        sys.modules.update({"matplotlib": mpl, "matplotlib.pyplot": plt})
+    if "omegaconf" not in sys.modules:
+        oc = types.ModuleType("omegaconf")
+        ocl = types.ModuleType("omegaconf.listconfig")
+        ocl.ListConfig = type("ListConfig", (list,), {})
+        oc.listconfig = ocl
+        sys.modules.update({"omegaconf": oc, "omegaconf.listconfig": ocl})
+    import torch
+    if torch.cuda.device_count() == 0:
+        torch.cuda.device_count = lambda: 1  # lib/sync.py:31-41 divides by device_count()
+
+
+_imported = False
+
+
+def import_reference():
+    """chdir into the reference tree (cfg_helper resolves 'configs/model' relative to CWD) and import."""
+    global _imported
+    install_shims()
+    if not _imported:
+        os.chdir(REF)
+        sys.path.insert(0, REF)
+        _imported = True
+    from lib.cfg_helper import model_cfg_bank
+    from lib.model_zoo import get_model
+    return model_cfg_bank, get_model
+
+
+def build_reference_net(name="pfd_seecoder_with_controlnet", overrides=None):
+    """Build the reference pipeline (random init).  `overrides(cfgm)` may shrink the config."""
+    import torch
+    model_cfg_bank, get_model = import_reference()
+    cfgm = model_cfg_bank()(name)
+    cfgm.args.vae_cfg_list[0][1].pop("pth", None)  # autokl.yaml:26 points to an absent checkpoint
+    if overrides is not None:
+        overrides(cfgm)
+    torch.manual_seed(0)
+    net = get_model()(cfgm)
+    net.eval()
+    return net, cfgm
+
+
+def cpu_sampler(net):
+    """DDIMSampler whose register_buffer does not force .to('cuda') (ddim.py:17-21)."""
+    from lib.model_zoo.ddim import DDIMSampler
+
+    class CPUSampler(DDIMSampler):
+        def register_buffer(self, name, attr):
+            setattr(self, name, attr)
+
+    return CPUSampler(net)
