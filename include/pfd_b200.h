@@ -86,7 +86,8 @@ typedef struct pfd_gemm_desc {
   float alpha;
   int32_t act;
   const void* bias;          /* [N] fp16 or NULL */
-  const void* rowadd;        /* [NB, N] fp16 or NULL: per-image broadcast add (time embedding) */
+  const void* rowadd;        /* [NB, >=N] fp16 or NULL: per-image broadcast add (time embedding) */
+  int64_t rowadd_ld;         /* row pitch of rowadd in elements (0 = N) */
   const void* residual;      /* same addressing as out, or NULL */
 
   void* out;                 /* fp16 */
@@ -178,6 +179,11 @@ PFD_API int pfd_window_scatter_f16(const void* win, int32_t B, int32_t H, int32_
 /* PatchMerging 2x2 gather -> [B, H/2*W/2, 4C] in the reference's x0,x1,x2,x3 order (swin.py:341-346). */
 PFD_API int pfd_patch_merge_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C,
                                void* out, void* stream);
+
+/* PatchEmbed gather (swin.py:479-489): NCHW image (fp16/fp32) -> [B, ceil(H/P), ceil(W/P), Kpad] rows in
+ * the K order of the flattened conv weight [O, C*P*P]; zero padding for ragged H/W and K..Kpad. */
+PFD_API int pfd_patchify_f16(const void* x, int32_t src_is_f32, int32_t B, int32_t C, int32_t H,
+                             int32_t W, int32_t P, int32_t Kpad, void* out, void* stream);
 
 #ifdef __cplusplus
 }

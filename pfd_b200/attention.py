@@ -1,0 +1,72 @@
+"""Multi-head attention on the C-ABI kernels (token-major fp16 tensors).
+
+``project_heads`` runs the q/k/v projection GEMM whose epilogue scatters straight into the per-head
+layouts the score/PV GEMMs consume (no transpose kernels):
+    q, k : [B*heads, N, d]          (d contiguous = K-major operand of Q K^T)
+    v^T  : [B*heads, d, Npad]       (keys contiguous = K-major B operand of P V)
+``attend`` = batched Q K^T -> fp16 scores -> row softmax (reference rounding points, optional
+relative-position bias / shift mask) -> batched P V written back as [B, Nq, heads*d].
+
+Reference call sites: attention.py:178-201 (UNet/ControlNet CrossAttention), swin.py:179-210
+(WindowAttention), seecoder.py:111,161 (nn.MultiheadAttention), autokl_modules.py:178-202.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native as nv
+
+
+def ceil8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def project_heads(x2d: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], B: int, N: int,
+                  heads: int, d: int, *, transposed: bool = False, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x2d [B*N, Cin] @ w[heads*d, Cin]^T (+b) -> [B*heads, Np, d] (or [B*heads, d, Np] if transposed).
+    Np = ceil8(N); pad rows/cols are zero."""
+    Np = ceil8(N)
+    dev = x2d.device
+    alloc = torch.zeros if Np != N else torch.empty
+    if transposed:
+        out = alloc((B * heads, d, Np), device=dev, dtype=torch.float16)
+        so = (heads * d * Np, 0, 0, 1, d * Np, Np)
+    else:
+        out = alloc((B * heads, Np, d), device=dev, dtype=torch.float16)
+        so = (heads * Np * d, 0, 0, d, Np * d, 1)
+    ld = x2d.stride(0)
+    segs = [(x2d, 1, x2d.shape[1], (ld, ld * N, ld * N))]
+    if x2 is not None:
+        segs.append((x2, 1, x2.shape[1], (x2.stride(0), x2.stride(0) * N, x2.stride(0) * N)))
+    nv.gemm_raw(segs, in_w=N, in_h=1, stride=1, W=N, H=1, NB=B, w=w, N=w.shape[0], K=w.stride(0), bias=b,
+                out=out, so=so, ndiv=1, cdiv=d)
+    return out
+
+
+def attend(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, B: int, heads: int, Nq: int, Nk: int,
+           scale: float, bias: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+           nwin: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [BH, Nqp, d], k [BH, Nkp, d], vt [BH, d, Nkp] -> out [B, Nq, heads*d]."""
+    BH, Nqp, d = q.shape
+    Nkp = k.shape[1]
+    dev = q.device
+    alloc = torch.zeros if Nkp != Nk else torch.empty
+    s = alloc((BH, Nq, Nkp), device=dev, dtype=torch.float16)
+    # S = Q K^T  (rows beyond Nq are not computed: the A raster is Nq wide)
+    nv.gemm_raw([(q, 1, d, (d, d * Nqp, d * Nqp))], in_w=Nq, in_h=1, stride=1, W=Nq, H=1, NB=BH, w=k,
+                N=Nkp, K=d, b_batch_stride=Nkp * d, out=s, so=(Nq * Nkp, 0, 0, Nkp, 0, 1))
+    nv.softmax_(_view_cols(s, Nk), scale, bias=bias, nheads=heads, mask=mask, nwin=nwin)
+    C = heads * d
+    if out is None:
+        out = torch.empty((B, Nq, C), device=dev, dtype=torch.float16)
+    # O = P V  -> [B, Nq, heads*d]
+    nv.gemm_raw([(s, 1, Nkp, (Nkp, Nkp * Nq, Nkp * Nq))], in_w=Nq, in_h=1, stride=1, W=Nq, H=1, NB=BH, w=vt,
+                N=d, K=Nkp, b_batch_stride=d * Nkp, out=out, so=(Nq * C, d, 0, C, 0, 1), ndiv=heads)
+    return out
+
+
+def _view_cols(s: torch.Tensor, cols: int) -> torch.Tensor:
+    # as_strided view keeps the row pitch (stride(1)) while exposing only the valid columns
+    return s.as_strided((s.shape[0], s.shape[1], cols), (s.stride(0), s.stride(1), 1))

@@ -1,0 +1,208 @@
+"""AutoencoderKL (decode path) on the pfd_b200 kernels — mirrors lib/model_zoo/autokl.py:14-54 and
+lib/model_zoo/autokl_modules.py:82-202, 368-568.
+
+The Encoder's parameters are kept (same names/shapes) so that reference VAE checkpoints load with
+strict=True, but only `decode` is on the hot path; `encode` raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import native as nv
+from .modules import Container, Conv2d, GroupNorm, pk_conv3, pk_conv3_small, pk_lin, pk_mat, pk_norm
+
+
+def Normalize(c):
+    return GroupNorm(32, c, eps=1e-6, affine=True)                       # autokl_modules.py:38-39
+
+
+class ResnetBlock(nn.Module):
+    """autokl_modules.py:82-141 (temb_channels=0, nin_shortcut when channels change)."""
+
+    def __init__(self, in_channels, out_channels=None):
+        super().__init__()
+        out_channels = out_channels or in_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.norm1 = Normalize(in_channels)
+        self.conv1 = Conv2d(in_channels, out_channels, 3, padding=1)
+        self.norm2 = Normalize(out_channels)
+        self.dropout = nn.Dropout(0.0)
+        self.conv2 = Conv2d(out_channels, out_channels, 3, padding=1)
+        if in_channels != out_channels:
+            self.nin_shortcut = Conv2d(in_channels, out_channels, 1)
+
+
+class AttnBlock(nn.Module):
+    """autokl_modules.py:150-202."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.in_channels = c
+        self.norm = Normalize(c)
+        self.q, self.k, self.v, self.proj_out = Conv2d(c, c, 1), Conv2d(c, c, 1), Conv2d(c, c, 1), Conv2d(c, c, 1)
+
+
+class _Resample(nn.Module):
+    def __init__(self, c, stride):
+        super().__init__()
+        self.with_conv = True
+        self.conv = Conv2d(c, c, 3, stride=stride, padding=1 if stride == 1 else 0)
+
+
+class Encoder(nn.Module):
+    """Parameter-only mirror of autokl_modules.py:368-459 (not on the hot path)."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, **_):
+        super().__init__()
+        self.conv_in = Conv2d(in_channels, ch, 3, padding=1)
+        in_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        bi = ch
+        for lvl in range(len(ch_mult)):
+            lv = Container()
+            lv.block = nn.ModuleList()
+            lv.attn = nn.ModuleList()
+            bi, bo = ch * in_mult[lvl], ch * ch_mult[lvl]
+            for _ in range(num_res_blocks):
+                lv.block.append(ResnetBlock(bi, bo))
+                bi = bo
+            if lvl != len(ch_mult) - 1:
+                lv.downsample = _Resample(bi, 2)
+            self.down.append(lv)
+        self.mid = Container()
+        self.mid.block_1, self.mid.attn_1, self.mid.block_2 = ResnetBlock(bi), AttnBlock(bi), ResnetBlock(bi)
+        self.norm_out = Normalize(bi)
+        self.conv_out = Conv2d(bi, 2 * z_channels if double_z else z_channels, 3, padding=1)
+
+
+class Decoder(nn.Module):
+    """autokl_modules.py:462-568."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, **_):
+        super().__init__()
+        if attn_resolutions:
+            raise NotImplementedError("pfd_b200 VAE decoder: attn_resolutions must be empty (autokl.yaml)")
+        self.ch, self.num_resolutions, self.num_res_blocks = ch, len(ch_mult), num_res_blocks
+        self.out_ch = out_ch
+        block_in = ch * ch_mult[-1]
+        self.conv_in = Conv2d(z_channels, block_in, 3, padding=1)
+        self.mid = Container()
+        self.mid.block_1, self.mid.attn_1, self.mid.block_2 = ResnetBlock(block_in), AttnBlock(block_in), ResnetBlock(block_in)
+        self.up = nn.ModuleList()
+        for lvl in reversed(range(self.num_resolutions)):
+            up = Container()
+            up.block = nn.ModuleList()
+            up.attn = nn.ModuleList()
+            block_out = ch * ch_mult[lvl]
+            for _ in range(num_res_blocks + 1):
+                up.block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+            if lvl != 0:
+                up.upsample = _Resample(block_in, 1)
+            self.up.insert(0, up)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = Conv2d(block_in, out_ch, 3, padding=1)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_vae_resnet(rb: ResnetBlock, x: torch.Tensor) -> torch.Tensor:
+    g, b = pk_norm(rb.norm1)
+    h = nv.groupnorm(x, g, b, rb.norm1.eps, silu=True)
+    w, bb = pk_conv3(rb.conv1)
+    h = nv.conv3x3(h, w, bb)
+    g, b = pk_norm(rb.norm2)
+    h = nv.groupnorm(h, g, b, rb.norm2.eps, silu=True)
+    if rb.in_channels != rb.out_channels:
+        w, bb = pk_conv3(rb.conv2, rb.nin_shortcut)
+        return nv.conv3x3(h, w, bb, skip=[x])
+    w, bb = pk_conv3(rb.conv2)
+    return nv.conv3x3(h, w, bb, residual=x)
+
+
+def run_vae_attn(at: AttnBlock, x: torch.Tensor) -> torch.Tensor:
+    """Single-head attention over H*W tokens with d = C (autokl_modules.py:178-202): scores are
+    materialised in fp16 exactly like the reference's bmm -> *c^-0.5 -> softmax -> bmm."""
+    B, H, W, C = x.shape
+    N = H * W
+    g, b = pk_norm(at.norm)
+    hn = nv.groupnorm(x, g, b, at.norm.eps, silu=False).reshape(B * N, C)
+    wq, bq = pk_lin(at.q)
+    wk, bk = pk_lin(at.k)
+    wv, bv = pk_lin(at.v)
+    q = nv.linear(hn, wq, bq).reshape(B, N, C)
+    k = nv.linear(hn, wk, bk).reshape(B, N, C)
+    vt = torch.empty((B, C, N), device=x.device, dtype=torch.float16)
+    nv.gemm_raw([(hn, 1, C, (C, C * N, C * N))], in_w=N, in_h=1, stride=1, W=N, H=1, NB=B, w=wv, N=C, K=C,
+                bias=bv, out=vt, so=(C * N, 0, 0, 1, 0, N))
+    s = torch.empty((B, N, N), device=x.device, dtype=torch.float16)
+    nv.bmm_nt(q, k, out=s, so=(N * N, 0, 0, N, 0, 1))
+    nv.softmax_(s, float(C) ** -0.5)
+    o = torch.empty((B, N, C), device=x.device, dtype=torch.float16)
+    nv.bmm_nt(s, vt, out=o, so=(N * C, 0, 0, C, 0, 1))
+    w, bb = pk_lin(at.proj_out)
+    return nv.linear(o.reshape(B * N, C), w, bb, residual=x.reshape(B * N, C)).reshape(B, H, W, C)
+
+
+class AutoencoderKL(nn.Module):
+    """autokl.py:14-54."""
+
+    def __init__(self, ddconfig, lossconfig=None, embed_dim=4, **_):
+        super().__init__()
+        assert ddconfig["double_z"]
+        self.encoder = Encoder(**ddconfig)
+        self.decoder = Decoder(**ddconfig)
+        self.quant_conv = Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
+        self.post_quant_conv = Conv2d(embed_dim, ddconfig["z_channels"], 1)
+        self.embed_dim = embed_dim
+
+    def encode(self, *a, **k):
+        raise NotImplementedError("VAE encode is outside the pfd_b200 hot path (SURVEY.md §8f)")
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, pre_scale: float = 1.0) -> torch.Tensor:
+        """autokl.py:44-54: post_quant_conv -> Decoder -> (x+1)/2 -> clamp.  z: NCHW latents (already
+        divided by the latent scale unless `pre_scale` carries 1/scale).  Returns NCHW fp16 in [0,1]."""
+        dec = self.decoder
+        B, Cz, H, W = z.shape
+        zc = nv.nchw_to_nhwc(z if z.dtype == torch.float32 else z.to(torch.float16), cpad=8)
+        wq, bq = pk_lin(self.post_quant_conv)                              # [8, 8] zero-padded 4x4
+        h = nv.linear(zc.reshape(B * H * W, 8), wq, bq, alpha=pre_scale).reshape(B, H, W, 8)
+        w, b, kpad = cached_conv_in(dec.conv_in, Cz)
+        col = nv.im2col3x3(h, kpad)
+        h = nv.linear(col.reshape(B * H * W, kpad), w, b).reshape(B, H, W, w.shape[0])
+        h = run_vae_resnet(dec.mid.block_1, h)
+        h = run_vae_attn(dec.mid.attn_1, h)
+        h = run_vae_resnet(dec.mid.block_2, h)
+        for lvl in reversed(range(dec.num_resolutions)):
+            up = dec.up[lvl]
+            for rb in up.block:
+                h = run_vae_resnet(rb, h)
+            if lvl != 0:
+                w, b = pk_conv3(up.upsample.conv)
+                h = nv.conv3x3(nv.upsample2x(h), w, b)
+        g, b = pk_norm(dec.norm_out)
+        h = nv.groupnorm(h, g, b, dec.norm_out.eps, silu=True)
+        w, b = pk_conv3(dec.conv_out)                                      # rows padded 3 -> 8
+        h = nv.conv3x3(h, w, b)
+        return nv.nhwc_to_nchw(h, dec.out_ch, mul=0.5, add=0.5, lo=0.0, hi=1.0)
+
+    def forward(self, z):
+        return self.decode(z)
+
+
+def cached_conv_in(conv: Conv2d, cz: int):
+    """conv_in consumes the 8-channel (zero-padded) post_quant output: pack [O, 9*8] with zero columns
+    for the pad channels so the im2col row (k = tap*8 + c) lines up."""
+    from .modules import _h, cached
+
+    def build():
+        o = conv.weight.shape[0]
+        w = torch.zeros((o, 3, 3, 8), device=conv.weight.device, dtype=torch.float16)
+        w[..., :cz] = _h(conv.weight).permute(0, 2, 3, 1)
+        return w.reshape(o, 72).contiguous(), _h(conv.bias), 72
+    return cached(conv, "conv_in8", [conv.weight, conv.bias], build)

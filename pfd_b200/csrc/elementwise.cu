@@ -509,6 +509,32 @@ __global__ void patch_merge_kernel(const uint4* __restrict__ x, int B, int H, in
   }
 }
 
+
+// PatchEmbed gather (swin.py:479-489): zero-pad H,W to multiples of P, then
+// out[b, py, px, (c*P + dy)*P + dx] = img[b, c, py*P+dy, px*P+dx]  (K order == flattened conv weight)
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ x, int B, int C, int H, int W, int P, int Kpad,
+                                __half* __restrict__ out) {
+  const int Hp = (H + P - 1) / P, Wp = (W + P - 1) / P;
+  const long long total = (long long)B * Hp * Wp * Kpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    long long p = i / Kpad;
+    const int px = (int)(p % Wp);
+    p /= Wp;
+    const int py = (int)(p % Hp);
+    const int b = (int)(p / Hp);
+    float v = 0.f;
+    if (k < C * P * P) {
+      const int dx = k % P, dy = (k / P) % P, c = k / (P * P);
+      const int y = py * P + dy, xx = px * P + dx;
+      if (y < H && xx < W) v = (float)x[(((long long)b * C + c) * H + y) * W + xx];
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
 static inline int grid_for(long long total, int threads) {
   long long g = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -552,7 +578,7 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
 extern "C" PFD_API int pfd_layernorm_f16(const void* x, const void* res, int64_t rows, int32_t C,
                                  const void* gamma, const void* beta, float eps, void* out,
                                  void* stream) {
-  if (C % 8 || C > 8 * 32 * 8) return set_error("pfd_layernorm_f16: C=%d unsupported", C);
+  if (C % 8 || C > 8 * 32 * 16) return set_error("pfd_layernorm_f16: C=%d unsupported", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
@@ -565,7 +591,8 @@ extern "C" PFD_API int pfd_layernorm_f16(const void* x, const void* res, int64_t
   if (vecs <= 32) layernorm_kernel<1><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
   else if (vecs <= 64) layernorm_kernel<2><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
   else if (vecs <= 128) layernorm_kernel<4><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
-  else layernorm_kernel<8><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
+  else if (vecs <= 256) layernorm_kernel<8><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
+  else layernorm_kernel<16><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
   return check_launch("layernorm");
 }
 
@@ -688,4 +715,16 @@ extern "C" PFD_API int pfd_patch_merge_gather_f16(const void* x, int32_t B, int3
   patch_merge_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), B, H, W, C / 8, static_cast<uint4*>(out));
   return check_launch("patch_merge");
+}
+
+extern "C" PFD_API int pfd_patchify_f16(const void* x, int32_t src_is_f32, int32_t B, int32_t C, int32_t H,
+                                        int32_t W, int32_t P, int32_t Kpad, void* out, void* stream) {
+  if (Kpad < C * P * P || Kpad % 8) return set_error("pfd_patchify_f16: Kpad=%d for C=%d P=%d", Kpad, C, P);
+  const long long total = (long long)B * ((H + P - 1) / P) * ((W + P - 1) / P) * Kpad;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src_is_f32)
+    patchify_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(x), B, C, H, W, P, Kpad, static_cast<__half*>(out));
+  else
+    patchify_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(x), B, C, H, W, P, Kpad, static_cast<__half*>(out));
+  return check_launch("patchify");
 }

@@ -47,6 +47,7 @@ struct alignas(64) GemmParams {
   const __half* residual;
   __half* out;
   long long so_n1, so_n0, so_y, so_x, so_c1, so_c0;
+  long long rowadd_ld;
   int ndiv, cdiv;
   int vec_ok;
 };
@@ -278,7 +279,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             }
             if (p.rowadd) {
               float rv[8];
-              load8h(p.rowadd + (long long)n * p.N + col, rv);
+              load8h(p.rowadd + (long long)n * p.rowadd_ld + col, rv);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += rv[i];
             }
@@ -420,6 +421,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   p.bias = static_cast<const __half*>(d->bias);
   p.rowadd = static_cast<const __half*>(d->rowadd);
   p.residual = static_cast<const __half*>(d->residual);
+  p.rowadd_ld = d->rowadd_ld > 0 ? d->rowadd_ld : d->N;
   p.out = static_cast<__half*>(d->out);
   p.so_n1 = d->so_n1; p.so_n0 = d->so_n0; p.so_y = d->so_y; p.so_x = d->so_x;
   p.so_c1 = d->so_c1; p.so_c0 = d->so_c0;
@@ -429,7 +431,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
              (d->so_y % 8 == 0) && (d->so_x % 8 == 0) && (d->so_c1 % 8 == 0) &&
              ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0);
-  if ((reinterpret_cast<uintptr_t>(d->bias) & 15) || (reinterpret_cast<uintptr_t>(d->rowadd) & 15))
+  if ((reinterpret_cast<uintptr_t>(d->bias) & 15) || (reinterpret_cast<uintptr_t>(d->rowadd) & 15) || (d->rowadd_ld % 8))
     return set_error("pfd_gemm_f16: bias/rowadd must be 16-byte aligned");
 
   // ---- output raster tiling: 128 rows = bw x bh x bn pixels, minimise padded work

@@ -26,7 +26,7 @@ EXPORTS = [
     "pfd_layernorm_f16", "pfd_softmax_f16", "pfd_timestep_embedding_f16", "pfd_upsample2x_f16",
     "pfd_nchw_to_nhwc_f16", "pfd_nhwc_to_nchw_f16", "pfd_im2col3x3_f16", "pfd_axpby_f16",
     "pfd_add_rowvec_f16", "pfd_ddim_step_f16", "pfd_window_gather_f16", "pfd_window_scatter_f16",
-    "pfd_patch_merge_gather_f16",
+    "pfd_patch_merge_gather_f16", "pfd_patchify_f16",
 ]
 
 
@@ -51,6 +51,7 @@ class GemmDesc(ctypes.Structure):
         ("act", c_int32),
         ("bias", c_void_p),
         ("rowadd", c_void_p),
+        ("rowadd_ld", c_int64),
         ("residual", c_void_p),
         ("out", c_void_p),
         ("so_n1", c_int64), ("so_n0", c_int64), ("so_y", c_int64), ("so_x", c_int64),
@@ -102,6 +103,8 @@ def load() -> ctypes.CDLL:
                                            c_void_p, c_void_p, c_void_p]
     lib.pfd_patch_merge_gather_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                                c_void_p]
+    lib.pfd_patchify_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_void_p, c_void_p]
     if hasattr(lib, "pfd_flash_attn_f16"):
         lib.pfd_flash_attn_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                            c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
@@ -165,6 +168,7 @@ def gemm_raw(segs: Sequence[Tuple[torch.Tensor, int, int, Tuple[int, int, int]]]
     d.alpha, d.act = alpha, act
     d.bias = _p(bias)
     d.rowadd = _p(rowadd)
+    d.rowadd_ld = rowadd.stride(0) if rowadd is not None else 0
     d.residual = _p(residual)
     d.out = out.data_ptr()
     d.so_n1, d.so_n0, d.so_y, d.so_x, d.so_c1, d.so_c0 = so
@@ -411,4 +415,16 @@ def patch_merge_gather(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((B, (H + 1) // 2, (W + 1) // 2, 4 * C), device=x.device, dtype=torch.float16)
     _check(load().pfd_patch_merge_gather_f16(x.data_ptr(), B, H, W, C, out.data_ptr(), stream_ptr()),
            "pfd_patch_merge_gather_f16")
+    return out
+
+
+def patchify(img: torch.Tensor, P: int, kpad: int) -> torch.Tensor:
+    """NCHW image (fp16/fp32) -> [B, ceil(H/P), ceil(W/P), kpad] patch rows (see pfd_patchify_f16)."""
+    B, C, H, W = img.shape
+    img = img.contiguous()
+    if img.dtype not in (torch.float16, torch.float32):
+        img = img.to(torch.float16)
+    out = torch.empty((B, -(-H // P), -(-W // P), kpad), device=img.device, dtype=torch.float16)
+    _check(load().pfd_patchify_f16(img.data_ptr(), int(img.dtype == torch.float32), B, C, H, W, P, kpad,
+                                   out.data_ptr(), stream_ptr()), "pfd_patchify_f16")
     return out

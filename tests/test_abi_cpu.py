@@ -36,7 +36,7 @@ def test_gemm_desc_layout_matches_header():
     d = native.GemmDesc()
     # 1+3+3 int32 (=28, pad to 32) + 3 ptr + 9 int64 + 6 int32 + ptr + int32(+pad) + 2 int64 + float + int32
     # + 4 ptr + 6 int64 + 3 int32 (+pad) + ptr
-    assert ctypes.sizeof(d) == 32 + 24 + 72 + 24 + 8 + 8 + 16 + 8 + 32 + 48 + 16 + 8
+    assert ctypes.sizeof(d) == 32 + 24 + 72 + 24 + 8 + 8 + 16 + 8 + 40 + 48 + 16 + 8
 
 
 def test_bad_descriptor_is_rejected_without_gpu():
