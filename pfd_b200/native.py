@@ -126,8 +126,18 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_replayed = 0
+
+
+def note_replay(n: int) -> None:
+    """Account for kernels re-launched by a CUDA-graph replay (they bypass the library's counter)."""
+    global _replayed
+    _replayed += int(n)
+
+
 def launch_count() -> int:
-    return int(load().pfd_launch_count())
+    """Kernels launched by this library in this process (direct launches + graph-replayed ones)."""
+    return int(load().pfd_launch_count()) + _replayed
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
