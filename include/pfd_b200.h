@@ -180,6 +180,19 @@ PFD_API int pfd_window_scatter_f16(const void* win, int32_t B, int32_t H, int32_
 PFD_API int pfd_patch_merge_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C,
                                void* out, void* stream);
 
+/*
+ * Fused flash attention (tcgen05): out[b, i, h*d + :] = softmax_j( fp16(q_i . k_j) * scale ) @ v  per (b, h),
+ * scores never leave the SM.  Replaces attention.py:186-201 (einsum -> softmax -> einsum) for the UNet /
+ * ControlNet self- and cross-attention.
+ *   q  [B*heads, q_rows, d]   (first Nq rows valid)      k [B*heads, k_rows, d] (first Nk rows valid)
+ *   vt [B*heads, d, vt_pitch] (V transposed, first Nk columns valid)
+ *   out element (b, i, h, c) at  b*o_sb + i*o_sq + h*d + c.       d % 8 == 0, d <= 192.
+ */
+PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const void* vt, void* out, int32_t B,
+                               int32_t heads, int32_t Nq, int32_t Nk, int32_t d, int32_t q_rows,
+                               int32_t k_rows, float scale, int64_t vt_pitch, int64_t o_sb, int64_t o_sq,
+                               int32_t reserved, void* stream);
+
 /* PatchEmbed gather (swin.py:479-489): NCHW image (fp16/fp32) -> [B, ceil(H/P), ceil(W/P), Kpad] rows in
  * the K order of the flattened conv weight [O, C*P*P]; zero padding for ragged H/W and K..Kpad. */
 PFD_API int pfd_patchify_f16(const void* x, int32_t src_is_f32, int32_t B, int32_t C, int32_t H,

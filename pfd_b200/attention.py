@@ -19,6 +19,11 @@ import torch
 from . import native as nv
 
 
+# fused tcgen05 flash attention for bias-free attention; False falls back to the materialised
+# QK^T GEMM -> softmax -> PV GEMM pipeline (still all pfd_b200 kernels) — used by tests to cross-check.
+USE_FLASH = True
+
+
 def ceil8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -52,6 +57,10 @@ def attend(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, B: int, heads:
     BH, Nqp, d = q.shape
     Nkp = k.shape[1]
     dev = q.device
+    if USE_FLASH and bias is None and mask is None and d <= 192:
+        if out is None:
+            out = torch.empty((B, Nq, heads * d), device=dev, dtype=torch.float16)
+        return nv.flash_attn(q, k, vt, B=B, heads=heads, Nq=Nq, Nk=Nk, scale=scale, out=out)
     alloc = torch.zeros if Nkp != Nk else torch.empty
     s = alloc((BH, Nq, Nkp), device=dev, dtype=torch.float16)
     # S = Q K^T  (rows beyond Nq are not computed: the A raster is Nq wide)

@@ -1,0 +1,370 @@
+// Fused flash attention for sm_100a (tcgen05 + TMEM + TMA), used for the UNet / ControlNet
+// self- and cross-attention (attention.py:178-201):  O = softmax(Q K^T * scale) V  per (batch, head)
+// without ever materialising the [N, Nk] score matrix in HBM.
+//
+//   CTA = 128 query rows of one (batch, head); KV processed in blocks of 64 keys.
+//   warp 0      : TMA producer (Q once; K / V^T blocks through a 2-stage ring)
+//   warp 1      : tcgen05.mma issuer   S_j = Q K_j^T  (TMEM, double buffered)   O += P_j V_j (TMEM)
+//   warps 2..5  : softmax: thread r owns query row r (TMEM lane r) -> no cross-thread reductions;
+//                 two passes over S_j in TMEM (max, then exp/sum), P_j written to shared memory in
+//                 the K-major 128B-swizzled layout the PV MMA reads, O rescaled in TMEM when the
+//                 running max moves, final O / l written as [B, Nq, heads*d].
+//   Scores are rounded exactly like the reference's fp16 pipeline: fp16(q.k) * scale -> fp16.
+//   Shared memory is kept small (60-152 KB) so two CTAs share an SM for d <= 80 and overlap each
+//   other's softmax (MUFU/ALU) and MMA phases.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/pfd_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pfd {
+
+constexpr int FA_BQ = 128;
+constexpr int FA_BKV = 64;
+constexpr int FA_THREADS = 192;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct alignas(64) FlashParams {
+  CUtensorMap tmQ, tmK, tmV;
+  int Nq, Nk, heads, d;
+  int nblk;
+  float scale;
+  __half* out;
+  long long o_sb, o_sq, o_sh;  // element strides: batch, query row, head
+};
+
+template <int DCH>
+struct FlashCfg {
+  static constexpr int Q_BYTES = DCH * FA_BQ * 128;
+  static constexpr int K_BYTES = DCH * FA_BKV * 128;
+  static constexpr int DN = DCH == 1 ? 64 : (DCH == 2 ? 128 : 192);  // max padded head dim
+  static constexpr int P_BYTES = FA_BQ * 128;
+  static constexpr uint32_t TMEM_COLS = (128 + DN <= 256) ? 256u : 512u;
+  // V^T stage = dN rows x 128 B (dN = ceil16(d), runtime) so d=80 still fits two CTAs per SM
+  static int smem_bytes(int dN) { return Q_BYTES + 2 * (K_BYTES + dN * 128) + P_BYTES + 1024 + 128; }
+};
+
+template <int DCH>
+__global__ void __launch_bounds__(FA_THREADS)
+flash_attn_kernel(const __grid_constant__ FlashParams p) {
+  using Cfg = FlashCfg<DCH>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const int d = p.d;
+  const int dN = (d + 15) & ~15;       // PV MMA N (rows of the V^T tile)
+  const int V_BYTES = dN * 128;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + Cfg::Q_BYTES;                  // [2][K_BYTES]
+  const uint32_t sV = sK + 2 * Cfg::K_BYTES;              // [2][V_BYTES]
+  const uint32_t sP = sV + 2 * V_BYTES;
+  const uint32_t bars = sP + Cfg::P_BYTES;
+  uint8_t* gP = gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES;
+  const uint32_t bar_q = bars;
+  auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto bar_kv_empty = [&](int s) { return bars + 8u * (3 + s); };
+  auto bar_s_full = [&](int s) { return bars + 8u * (5 + s); };
+  auto bar_s_free = [&](int s) { return bars + 8u * (7 + s); };
+  const uint32_t bar_p_ready = bars + 8u * 9;
+  const uint32_t bar_pv_done = bars + 8u * 10;
+  const uint32_t tmem_slot = bars + 8u * 11;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(
+      gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES + Cfg::P_BYTES + 8 * 11);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FA_BQ;
+  const int bh = blockIdx.y;
+  const int nblk = p.nblk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_kv_full(s), 1);
+      mbar_init(bar_kv_empty(s), 1);
+      mbar_init(bar_s_full(s), 1);
+      mbar_init(bar_s_free(s), 128);
+    }
+    mbar_init(bar_p_ready, 128);
+    mbar_init(bar_pv_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+      for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + c * FA_BQ * 128, &p.tmQ, bar_q, c * 64, q0, bh);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1, u = j >> 1;
+        if (u >= 1) mbar_wait(bar_kv_empty(st), (u - 1) & 1);
+        mbar_expect_tx(bar_kv_full(st), Cfg::K_BYTES + V_BYTES);
+        for (int c = 0; c < DCH; ++c)
+          tma_load_3d(sK + st * Cfg::K_BYTES + c * FA_BKV * 128, &p.tmK, bar_kv_full(st), c * 64, j * FA_BKV, bh);
+        tma_load_3d(sV + st * V_BYTES, &p.tmV, bar_kv_full(st), j * FA_BKV, 0, bh);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(FA_BKV);
+      const uint32_t idesc_o = make_idesc_f16((uint32_t)dN);
+      auto issue_S = [&](int j) {
+        const int st = j & 1;
+        const uint32_t tS = tmem_base + st * FA_BKV;
+        bool first = true;
+        for (int c = 0; c < DCH; ++c) {
+          const int rem = d - c * 64;
+          if (rem <= 0) break;
+          const int ksteps = rem >= 64 ? 4 : (rem + 15) / 16;
+          const uint64_t ad = make_sw128_kmajor_desc(sQ + c * FA_BQ * 128);
+          const uint64_t bd = make_sw128_kmajor_desc(sK + st * Cfg::K_BYTES + c * FA_BKV * 128);
+          for (int s = 0; s < ksteps; ++s) {
+            umma_f16(tS, ad + 2u * s, bd + 2u * s, idesc_s, first ? 0u : 1u);
+            first = false;
+          }
+        }
+        umma_commit(bar_s_full(st));
+      };
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv_full(0), 0);
+      tc_fence_after();
+      issue_S(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {
+          const int st = (j + 1) & 1, u = (j + 1) >> 1;
+          mbar_wait(bar_kv_full(st), u & 1);
+          if (u >= 1) mbar_wait(bar_s_free(st), (u - 1) & 1);
+          tc_fence_after();
+          issue_S(j + 1);
+        }
+        mbar_wait(bar_p_ready, j & 1);
+        tc_fence_after();
+        const int st = j & 1;
+        const uint64_t ad = make_sw128_kmajor_desc(sP);
+        const uint64_t bd = make_sw128_kmajor_desc(sV + st * V_BYTES);
+#pragma unroll
+        for (int s = 0; s < FA_BKV / 16; ++s)
+          umma_f16(tmem_O, ad + 2u * s, bd + 2u * s, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
+        umma_commit(bar_kv_empty(st));
+        umma_commit(bar_pv_done);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / output warps
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    uint8_t* prow = gP + row * 128;
+    const int rsw = row & 7;
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j & 1, u = j >> 1;
+      const int kvalid = min(FA_BKV, p.Nk - j * FA_BKV);
+      mbar_wait(bar_s_full(st), u & 1);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + lane_off + st * FA_BKV;
+      // pass 1: row max of the fp16-rounded, scaled scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < FA_BKV / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(tS + c * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (c * 16 + i < kvalid) {
+            float v = __half2float(__float2half_rn(__uint_as_float(r[i])));
+            v = __half2float(__float2half_rn(v * p.scale));
+            mx = fmaxf(mx, v);
+          }
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - m_new) * LOG2E);
+      if (j > 0) {
+        mbar_wait(bar_pv_done, (j - 1) & 1);   // PV_{j-1} finished: P buffer free, O stable
+        tc_fence_after();
+      }
+      // pass 2: p = exp(v - m_new), row sum, P -> shared memory (swizzled K-major A operand)
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < FA_BKV / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(tS + c * 16, r);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float pv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float v = __half2float(__float2half_rn(__uint_as_float(r[i + e])));
+            v = __half2float(__float2half_rn(v * p.scale));
+            pv[e] = (c * 16 + i + e < kvalid) ? fast_exp2((v - m_new) * LOG2E) : 0.f;
+          }
+          __half2 h2 = __floats2half2_rn(pv[0], pv[1]);
+          // accumulate the row sum from the rounded values that the PV MMA will actually consume
+          float2 back = __half22float2(h2);
+          sum += back.x + back.y;
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        const int g0 = c * 2;
+        *reinterpret_cast<uint4*>(prow + (((g0) ^ rsw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(prow + (((g0 + 1) ^ rsw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_s_free(st));
+      l = l * alpha + sum;
+      m = m_new;
+      // rescale the running output when this warp's maxima moved
+      if (j > 0) {
+        const bool need = __any_sync(0xffffffffu, alpha != 1.f);
+        if (need) {
+          for (int c = 0; c < dN / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_off + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_off + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready);
+    }
+    // ---- epilogue: O / l -> [B, Nq, heads*d]
+    mbar_wait(bar_pv_done, (nblk - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + row;
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const int b = bh / p.heads, h = bh % p.heads;
+    __half* orow = p.out + (long long)b * p.o_sb + (long long)q * p.o_sq + (long long)h * p.o_sh;
+    for (int c = 0; c < dN / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_off + c * 16, o);
+      tmem_ld_wait();
+      if (q < p.Nq) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int col = c * 16 + h8 * 8;
+          if (col < d) {
+            uint4 v;
+            __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              hv[i] = __floats2half2_rn(__uint_as_float(o[h8 * 8 + 2 * i]) * inv,
+                                        __uint_as_float(o[h8 * 8 + 2 * i + 1]) * inv);
+            *reinterpret_cast<uint4*>(orow + col) = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode3d(CUtensorMap* m, const void* ptr, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
+                    cuuint64_t s1_bytes, cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1, const char* what) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return set_error("cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(fp);
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error("flash attention tensor map (%s) encode failed: CUresult %d dims[%llu,%llu,%llu] strides[%llu,%llu] box[%u,%u]",
+                     what, (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                     (unsigned long long)s1_bytes, (unsigned long long)s2_bytes, b0, b1);
+  return 0;
+}
+
+template <int DCH>
+static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t st) {
+  using Cfg = FlashCfg<DCH>;
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::smem_bytes(Cfg::DN));
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(flash DCH=%d): %s", DCH, cudaGetErrorString(e));
+    done = true;
+  }
+  const int smem = Cfg::smem_bytes((p.d + 15) & ~15);
+  flash_attn_kernel<DCH><<<grid, FA_THREADS, smem, st>>>(p);
+  return check_launch("pfd_flash_attn_f16");
+}
+
+}  // namespace pfd
+
+using namespace pfd;
+
+extern "C" PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const void* vt, void* out, int32_t B,
+                                          int32_t heads, int32_t Nq, int32_t Nk, int32_t d, int32_t q_rows,
+                                          int32_t k_rows, float scale, int64_t vt_pitch, int64_t o_sb,
+                                          int64_t o_sq, int32_t reserved, void* stream) {
+  (void)reserved;
+  if (d % 8 || d <= 0 || d > 192) return set_error("pfd_flash_attn_f16: head dim %d unsupported", d);
+  if (Nq <= 0 || Nk <= 0) return set_error("pfd_flash_attn_f16: empty problem");
+  if (vt_pitch % 8) return set_error("pfd_flash_attn_f16: V^T pitch must be a multiple of 8");
+  FlashParams p;
+  memset(&p, 0, sizeof(p));
+  const long long BH = (long long)B * heads;
+  const int dN = (d + 15) & ~15;
+  if (int rc = encode3d(&p.tmQ, q, d, Nq, BH, (cuuint64_t)d * 2, (cuuint64_t)q_rows * d * 2, 64, FA_BQ, "Q")) return rc;
+  if (int rc = encode3d(&p.tmK, k, d, Nk, BH, (cuuint64_t)d * 2, (cuuint64_t)k_rows * d * 2, 64, FA_BKV, "K")) return rc;
+  if (int rc = encode3d(&p.tmV, vt, Nk, d, BH, (cuuint64_t)vt_pitch * 2, (cuuint64_t)d * vt_pitch * 2, 64, (cuuint32_t)dN, "V^T")) return rc;
+  p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.d = d;
+  p.nblk = (Nk + FA_BKV - 1) / FA_BKV;
+  p.scale = scale;
+  p.out = static_cast<__half*>(out);
+  p.o_sb = o_sb; p.o_sq = o_sq; p.o_sh = d;
+  dim3 grid((Nq + FA_BQ - 1) / FA_BQ, (unsigned)BH);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d <= 64) return launch_flash<1>(p, grid, st);
+  if (d <= 128) return launch_flash<2>(p, grid, st);
+  return launch_flash<3>(p, grid, st);
+}

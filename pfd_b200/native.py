@@ -26,7 +26,7 @@ EXPORTS = [
     "pfd_layernorm_f16", "pfd_softmax_f16", "pfd_timestep_embedding_f16", "pfd_upsample2x_f16",
     "pfd_nchw_to_nhwc_f16", "pfd_nhwc_to_nchw_f16", "pfd_im2col3x3_f16", "pfd_axpby_f16",
     "pfd_add_rowvec_f16", "pfd_ddim_step_f16", "pfd_window_gather_f16", "pfd_window_scatter_f16",
-    "pfd_patch_merge_gather_f16", "pfd_patchify_f16",
+    "pfd_patch_merge_gather_f16", "pfd_patchify_f16", "pfd_flash_attn_f16",
 ]
 
 
@@ -105,7 +105,7 @@ def load() -> ctypes.CDLL:
                                                c_void_p]
     lib.pfd_patchify_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p, c_void_p]
-    if hasattr(lib, "pfd_flash_attn_f16"):
+    if True:
         lib.pfd_flash_attn_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                            c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                            c_int64, c_int64, c_int64, c_int32, c_void_p]
@@ -437,4 +437,15 @@ def patchify(img: torch.Tensor, P: int, kpad: int) -> torch.Tensor:
     out = torch.empty((B, -(-H // P), -(-W // P), kpad), device=img.device, dtype=torch.float16)
     _check(load().pfd_patchify_f16(img.data_ptr(), int(img.dtype == torch.float32), B, C, H, W, P, kpad,
                                    out.data_ptr(), stream_ptr()), "pfd_patchify_f16")
+    return out
+
+
+def flash_attn(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, B: int, heads: int, Nq: int, Nk: int,
+               scale: float, out: torch.Tensor) -> torch.Tensor:
+    """Fused attention (see pfd_flash_attn_f16): q [BH, Nqp, d], k [BH, Nkp, d], vt [BH, d, Nkp] ->
+    out [B, Nq, heads*d]."""
+    d = q.shape[2]
+    _check(load().pfd_flash_attn_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Nq, Nk,
+                                     d, q.shape[1], k.shape[1], scale, vt.shape[2], out.stride(0), out.stride(1),
+                                     0, stream_ptr()), "pfd_flash_attn_f16")
     return out
