@@ -257,3 +257,31 @@ def test_ddim_step_matches_fp16_eager(nv):
     ref = a_p.sqrt() * pred + (1. - a_p - sg ** 2).sqrt() * e
     close(p0, pred, rtol=2e-3, atol=2e-3)
     close(xp, ref, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", [(2, 8, 4096, 4096, 40), (2, 8, 4096, 148, 40), (2, 8, 1024, 1024, 80),
+                                             (1, 8, 256, 256, 160), (1, 4, 100, 77, 40), (1, 8, 64, 64, 160),
+                                             (1, 2, 300, 130, 64), (1, 8, 144, 576, 96)])
+def test_flash_attention(nv, B, heads, Nq, Nk, d):
+    from pfd_b200 import attention as att
+    C = heads * d
+    x = rnd(B * Nq, C, scale=1.0)
+    ctx = rnd(B * Nk, C, scale=1.0, seed=3)
+    wq, wk, wv = (rnd(C, C, scale=C ** -0.5, seed=s) for s in (4, 5, 6))
+    q = att.project_heads(x, wq, None, B, Nq, heads, d)
+    k = att.project_heads(ctx, wk, None, B, Nk, heads, d)
+    vt = att.project_heads(ctx, wv, None, B, Nk, heads, d, transposed=True)
+    scale = d ** -0.5
+    att.USE_FLASH = True
+    o_flash = att.attend(q, k, vt, B=B, heads=heads, Nq=Nq, Nk=Nk, scale=scale)
+    att.USE_FLASH = False
+    o_unfused = att.attend(q, k, vt, B=B, heads=heads, Nq=Nq, Nk=Nk, scale=scale)
+    att.USE_FLASH = True
+    torch.cuda.synchronize()
+    qf = q[:, :Nq].float()
+    kf = k[:, :Nk].float()
+    vf = vt[:, :, :Nk].float().transpose(1, 2)
+    s = (torch.bmm(qf, kf.transpose(1, 2)).half().float() * scale).half().float()
+    ref = torch.bmm(torch.softmax(s, -1), vf).reshape(B, heads, Nq, d).permute(0, 2, 1, 3).reshape(B, Nq, C)
+    close(o_unfused, ref, rtol=6e-3, atol=2e-3)
+    close(o_flash, ref, rtol=6e-3, atol=2e-3)
