@@ -192,7 +192,9 @@ def gemm_roofline_pass(net, sampler_cls, cond, uncond, batch, L):
         e0.record()
         orig(segs, **kw)
         e1.record()
-        rec.append((2.0 * rows * kw["N"] * ktot, e0, e1))
+        rec.append((2.0 * rows * kw["N"] * ktot, e0, e1,
+                    dict(rows=rows, W=kw["W"], H=kw["H"], NB=kw["NB"], N=kw["N"], K=ktot, taps=[t for (_, t, _, _) in segs],
+                         stride=kw["stride"], act=kw.get("act", 0), batched=bool(kw.get("b_batch_stride", 0)))))
 
     c_full = torch.cat([uncond, cond])
     prep = net.prepare_context(c_full, "image")
@@ -209,6 +211,16 @@ def gemm_roofline_pass(net, sampler_cls, cond, uncond, batch, L):
         nv.gemm_raw = orig
     flops = sum(r[0] for r in rec)
     ms = sum(r[1].elapsed_time(r[2]) for r in rec)
+    dump = os.environ.get("PFD_BENCH_DUMP")
+    if dump:
+        rows = []
+        for fl, a, b, info in rec:
+            t = a.elapsed_time(b)
+            rows.append(dict(info, ms=t, tflops=fl / t / 1e9 if t > 0 else 0.0))
+        rows.sort(key=lambda r: -r["ms"])
+        with open(dump, "w") as f:
+            for r in rows:
+                f.write(json.dumps(r) + "\n")
     return flops, ms, len(rec)
 
 

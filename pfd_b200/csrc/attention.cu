@@ -9,7 +9,10 @@
 //                 two passes over S_j in TMEM (max, then exp/sum), P_j written to shared memory in
 //                 the K-major 128B-swizzled layout the PV MMA reads, O rescaled in TMEM when the
 //                 running max moves, final O / l written as [B, Nq, heads*d].
-//   Scores are rounded exactly like the reference's fp16 pipeline: fp16(q.k) * scale -> fp16.
+//   Logits are rounded to fp16 like the reference's fp16 score tensor (fp16(q.k * scale)); the softmax
+//   runs on packed half2 (HMNMX2 / HSUB2 / HMUL2 / MUFU.EX2.F16x2, two keys per instruction) and the row
+//   sum l comes for free from the tensor core: row d of the V^T tile is all ones, so column d of the
+//   O accumulator is sum_j p_j (rescaled together with O).
 //   Shared memory is kept small (60-152 KB) so two CTAs share an SM for d <= 80 and overlap each
 //   other's softmax (MUFU/ALU) and MMA phases.
 #include <cuda.h>
@@ -28,6 +31,11 @@ constexpr int FA_BQ = 128;
 constexpr int FA_BKV = 64;
 constexpr int FA_THREADS = 192;
 
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -47,10 +55,9 @@ template <int DCH>
 struct FlashCfg {
   static constexpr int Q_BYTES = DCH * FA_BQ * 128;
   static constexpr int K_BYTES = DCH * FA_BKV * 128;
-  static constexpr int DN = DCH == 1 ? 64 : (DCH == 2 ? 128 : 192);  // max padded head dim
+  static constexpr int DN = DCH == 1 ? 80 : (DCH == 2 ? 144 : 208);  // max rows of the V^T tile (d + ones row, padded)
   static constexpr int P_BYTES = FA_BQ * 128;
-  static constexpr uint32_t TMEM_COLS = (128 + DN <= 256) ? 256u : 512u;
-  // V^T stage = dN rows x 128 B (dN = ceil16(d), runtime) so d=80 still fits two CTAs per SM
+  // V^T stage = dN rows x 128 B (dN = ceil16(d + 1), runtime) so d=80 still fits two CTAs per SM
   static int smem_bytes(int dN) { return Q_BYTES + 2 * (K_BYTES + dN * 128) + P_BYTES + 1024 + 128; }
 };
 
@@ -63,8 +70,9 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
   const int d = p.d;
-  const int dN = (d + 15) & ~15;       // PV MMA N (rows of the V^T tile)
+  const int dN = (d + 16) & ~15;       // PV MMA N: d value rows + the all-ones row (-> row sums), padded to 16
   const int V_BYTES = dN * 128;
+  const uint32_t tmem_cols = (128 + dN <= 256) ? 256u : 512u;
   const uint32_t sQ = base;
   const uint32_t sK = sQ + Cfg::Q_BYTES;                  // [2][K_BYTES]
   const uint32_t sV = sK + 2 * Cfg::K_BYTES;              // [2][V_BYTES]
@@ -105,7 +113,19 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
     mbar_init(bar_pv_done, 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) tmem_alloc_rt(tmem_slot, tmem_cols);
+  if (warp >= 2) {
+    // rows d..dN-1 of both V^T stages are never written by TMA (its box has d rows): row d = ones, rest = 0
+    uint8_t* gV = gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES;
+    const int t = threadIdx.x - 64;
+    const int per_stage = (dN - d) * 8;               // 16-byte granules
+    for (int i = t; i < 2 * per_stage; i += 128) {
+      const int st = i / per_stage, g = i % per_stage;
+      const uint32_t word = (g < 8) ? 0x3C003C00u : 0u;
+      *reinterpret_cast<uint4*>(gV + st * V_BYTES + d * 128 + g * 16) = make_uint4(word, word, word, word);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -119,7 +139,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       for (int j = 0; j < nblk; ++j) {
         const int st = j & 1, u = j >> 1;
         if (u >= 1) mbar_wait(bar_kv_empty(st), (u - 1) & 1);
-        mbar_expect_tx(bar_kv_full(st), Cfg::K_BYTES + V_BYTES);
+        mbar_expect_tx(bar_kv_full(st), Cfg::K_BYTES + d * 128);
         for (int c = 0; c < DCH; ++c)
           tma_load_3d(sK + st * Cfg::K_BYTES + c * FA_BKV * 128, &p.tmK, bar_kv_full(st), c * 64, j * FA_BKV, bh);
         tma_load_3d(sV + st * V_BYTES, &p.tmV, bar_kv_full(st), j * FA_BKV, 0, bh);
@@ -176,39 +196,44 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f;
+    const float sc = p.scale;
+    const __half2 log2e2 = __float2half2_rn(LOG2E);
+    const __half2 ninf2 = __float2half2_rn(-INFINITY);
+    float m = -INFINITY;
     uint8_t* prow = gP + row * 128;
     const int rsw = row & 7;
     for (int j = 0; j < nblk; ++j) {
       const int st = j & 1, u = j >> 1;
       const int kvalid = min(FA_BKV, p.Nk - j * FA_BKV);
+      const bool partial = kvalid < FA_BKV;            // block-uniform
       mbar_wait(bar_s_full(st), u & 1);
       tc_fence_after();
       const uint32_t tS = tmem_base + lane_off + st * FA_BKV;
-      // pass 1: row max of the fp16-rounded, scaled scores
-      float mx = -INFINITY;
+      // pass 1: row max of the fp16 logits (two keys per HMNMX2)
+      __half2 mx2 = ninf2;
 #pragma unroll
       for (int c = 0; c < FA_BKV / 16; ++c) {
         uint32_t r[16];
         tmem_ld16(tS + c * 16, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (c * 16 + i < kvalid) {
-            float v = __half2float(__float2half_rn(__uint_as_float(r[i])));
-            v = __half2float(__float2half_rn(v * p.scale));
-            mx = fmaxf(mx, v);
+        for (int i = 0; i < 16; i += 2) {
+          __half2 v = __floats2half2_rn(__uint_as_float(r[i]) * sc, __uint_as_float(r[i + 1]) * sc);
+          if (partial) {
+            if (c * 16 + i >= kvalid) v = ninf2;
+            else if (c * 16 + i + 1 >= kvalid) v = __halves2half2(__low2half(v), __float2half_rn(-INFINITY));
           }
+          mx2 = __hmax2(mx2, v);
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2((m - m_new) * LOG2E);
+      const float m_new = fmaxf(m, fmaxf(__low2float(mx2), __high2float(mx2)));
+      const float alpha = (j == 0) ? 0.f : fast_exp2((m - m_new) * LOG2E);
+      const __half2 mh2 = __float2half2_rn(m_new);     // exact: m_new is an fp16 value
       if (j > 0) {
-        mbar_wait(bar_pv_done, (j - 1) & 1);   // PV_{j-1} finished: P buffer free, O stable
+        mbar_wait(bar_pv_done, (j - 1) & 1);           // PV_{j-1} finished: P buffer free, O stable
         tc_fence_after();
       }
-      // pass 2: p = exp(v - m_new), row sum, P -> shared memory (swizzled K-major A operand)
-      float sum = 0.f;
+      // pass 2: p = 2^((v - m) * log2e) on packed halves -> P tile in shared memory
 #pragma unroll
       for (int c = 0; c < FA_BKV / 16; ++c) {
         uint32_t r[16];
@@ -217,18 +242,13 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
-          float pv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            float v = __half2float(__float2half_rn(__uint_as_float(r[i + e])));
-            v = __half2float(__float2half_rn(v * p.scale));
-            pv[e] = (c * 16 + i + e < kvalid) ? fast_exp2((v - m_new) * LOG2E) : 0.f;
+          __half2 v = __floats2half2_rn(__uint_as_float(r[i]) * sc, __uint_as_float(r[i + 1]) * sc);
+          if (partial) {
+            if (c * 16 + i >= kvalid) v = ninf2;
+            else if (c * 16 + i + 1 >= kvalid) v = __halves2half2(__low2half(v), __float2half_rn(-INFINITY));
           }
-          __half2 h2 = __floats2half2_rn(pv[0], pv[1]);
-          // accumulate the row sum from the rounded values that the PV MMA will actually consume
-          float2 back = __half22float2(h2);
-          sum += back.x + back.y;
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+          const __half2 t = __hmul2(__hsub2(v, mh2), log2e2);
+          pk[i >> 1] = ex2_f16x2(*reinterpret_cast<const uint32_t*>(&t));
         }
         const int g0 = c * 2;
         *reinterpret_cast<uint4*>(prow + (((g0) ^ rsw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -236,9 +256,8 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       }
       tc_fence_before();
       mbar_arrive(bar_s_free(st));
-      l = l * alpha + sum;
       m = m_new;
-      // rescale the running output when this warp's maxima moved
+      // rescale the running output (and its row-sum column) when this warp's maxima moved
       if (j > 0) {
         const bool need = __any_sync(0xffffffffu, alpha != 1.f);
         if (need) {
@@ -257,14 +276,23 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       tc_fence_before();
       mbar_arrive(bar_p_ready);
     }
-    // ---- epilogue: O / l -> [B, Nq, heads*d]
+    // ---- epilogue: O / l -> [B, Nq, heads*d]   (l = column d of the accumulator)
     mbar_wait(bar_pv_done, (nblk - 1) & 1);
     tc_fence_after();
+    float l = 0.f;
+    {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_off + (d & ~15), o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (d & 15)) l = __uint_as_float(o[i]);
+    }
     const int q = q0 + row;
     const float inv = l > 0.f ? 1.f / l : 0.f;
     const int b = bh / p.heads, h = bh % p.heads;
     __half* orow = p.out + (long long)b * p.o_sb + (long long)q * p.o_sq + (long long)h * p.o_sh;
-    for (int c = 0; c < dN / 16; ++c) {
+    for (int c = 0; c < (d + 15) / 16; ++c) {
       uint32_t o[16];
       tmem_ld16(tmem_O + lane_off + c * 16, o);
       tmem_ld_wait();
@@ -289,7 +317,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    tmem_dealloc_rt(tmem_base, tmem_cols);
   }
 }
 
@@ -333,7 +361,7 @@ static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t st) {
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(flash DCH=%d): %s", DCH, cudaGetErrorString(e));
     done = true;
   }
-  const int smem = Cfg::smem_bytes((p.d + 15) & ~15);
+  const int smem = Cfg::smem_bytes((p.d + 16) & ~15);
   flash_attn_kernel<DCH><<<grid, FA_THREADS, smem, st>>>(p);
   return check_launch("pfd_flash_attn_f16");
 }
@@ -353,10 +381,9 @@ extern "C" PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const vo
   FlashParams p;
   memset(&p, 0, sizeof(p));
   const long long BH = (long long)B * heads;
-  const int dN = (d + 15) & ~15;
   if (int rc = encode3d(&p.tmQ, q, d, Nq, BH, (cuuint64_t)d * 2, (cuuint64_t)q_rows * d * 2, 64, FA_BQ, "Q")) return rc;
   if (int rc = encode3d(&p.tmK, k, d, Nk, BH, (cuuint64_t)d * 2, (cuuint64_t)k_rows * d * 2, 64, FA_BKV, "K")) return rc;
-  if (int rc = encode3d(&p.tmV, vt, Nk, d, BH, (cuuint64_t)vt_pitch * 2, (cuuint64_t)d * vt_pitch * 2, 64, (cuuint32_t)dN, "V^T")) return rc;
+  if (int rc = encode3d(&p.tmV, vt, Nk, d, BH, (cuuint64_t)vt_pitch * 2, (cuuint64_t)d * vt_pitch * 2, 64, (cuuint32_t)d, "V^T")) return rc;
   p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.d = d;
   p.nblk = (Nk + FA_BKV - 1) / FA_BKV;
   p.scale = scale;

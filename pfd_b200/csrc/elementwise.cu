@@ -41,13 +41,21 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ float rh(float v) { return __half2float(__float2half_rn(v)); }
 
 // ------------------------------------------------------------------------------------ GroupNorm
-// Pass 1: per-(image, group) sum and sum of squares.  grid = (chunks, NB); each CTA owns a pixel
-// range, threads stride over (pixel, 8-channel vector) pairs; group partials are reduced in shared
-// memory and flushed with one double atomicAdd per (group, CTA).
-constexpr int GN_THREADS = 256;
+// Thread mapping shared by both passes: blockDim is a multiple of the number of 8-channel vectors
+// (vecs = C/8) so a thread always owns the same channel vector and strides over pixels ->
+// consecutive threads read consecutive 16-byte vectors of one pixel (fully coalesced), per-channel
+// partial sums / affine coefficients live in registers, and nothing is recomputed per element.
+//   pass 1 (gn_stats): per-(image, group) sum / sum of squares -> fp64 atomics (one per group per CTA)
+//   pass 2 (gn_apply): y = x * a[c] + b[c] (a = rstd*gamma, b = beta - mean*a) [+ SiLU] -> fp16
 constexpr int GN_MAX_GROUPS = 32;
 
-__global__ void __launch_bounds__(GN_THREADS)
+__device__ __forceinline__ uint4 gn_load(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2,
+                                         int c2, long long pixn, int c) {
+  if (c < c1) return __ldg(reinterpret_cast<const uint4*>(x1 + pixn * c1 + c));
+  return __ldg(reinterpret_cast<const uint4*>(x2 + pixn * c2 + (c - c1)));
+}
+
+__global__ void __launch_bounds__(320)
 gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
                 long long HW, int groups, long long pix_per_cta, double* __restrict__ ws) {
   const int C = c1 + c2;
@@ -64,60 +72,70 @@ gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
     s_sq[threadIdx.x] = 0.f;
   }
   __syncthreads();
-  const long long items = (p1 - p0) * vecs;
-  // a thread keeps hitting the same channel vector when blockDim % vecs == 0; otherwise it varies,
-  // so accumulate per item into a small register cache keyed by the current group.
-  int cur_g = -1;
-  float acc_s = 0.f, acc_q = 0.f;
-  for (long long it = threadIdx.x; it < items; it += blockDim.x) {
-    const long long pix = p0 + it / vecs;
-    const int v = (int)(it % vecs);
+  const int lanes = blockDim.x / vecs;      // pixel lanes per CTA (blockDim % vecs == 0, or vecs > blockDim)
+  if (lanes >= 1) {
+    const int v = threadIdx.x % vecs;
     const int c = v * 8;
-    uint4 u;
-    if (c < c1)
-      u = __ldg(reinterpret_cast<const uint4*>(x1 + ((long long)n * HW + pix) * c1 + c));
-    else
-      u = __ldg(reinterpret_cast<const uint4*>(x2 + ((long long)n * HW + pix) * c2 + (c - c1)));
-    float f[8];
-    unpack8(u, f);
-    if (cpg % 8 == 0) {
-      const int g = c / cpg;
-      if (g != cur_g) {
-        if (cur_g >= 0) {
-          atomicAdd(&s_sum[cur_g], acc_s);
-          atomicAdd(&s_sq[cur_g], acc_q);
-        }
-        cur_g = g;
-        acc_s = 0.f;
-        acc_q = 0.f;
-      }
+    float sm[8], sq[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc_s += f[i];
-        acc_q += f[i] * f[i];
-      }
-    } else {
-      // group boundary may fall inside the vector (e.g. C=1920 -> 60 channels per group)
+    for (int i = 0; i < 8; ++i) sm[i] = sq[i] = 0.f;
+    long long pix = p0 + threadIdx.x / vecs;
+    for (; pix + 3 * lanes < p1; pix += 4 * lanes) {
+      uint4 u[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int g = (c + i) / cpg;
-        if (g != cur_g) {
-          if (cur_g >= 0) {
-            atomicAdd(&s_sum[cur_g], acc_s);
-            atomicAdd(&s_sq[cur_g], acc_q);
-          }
-          cur_g = g;
-          acc_s = 0.f;
-          acc_q = 0.f;
+      for (int k = 0; k < 4; ++k) u[k] = gn_load(x1, c1, x2, c2, (long long)n * HW + pix + k * lanes, c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sm[i] += f[i];
+          sq[i] += f[i] * f[i];
         }
-        acc_s += f[i];
-        acc_q += f[i] * f[i];
       }
     }
-  }
-  if (cur_g >= 0) {
-    atomicAdd(&s_sum[cur_g], acc_s);
-    atomicAdd(&s_sq[cur_g], acc_q);
+    for (; pix < p1; pix += lanes) {
+      float f[8];
+      unpack8(gn_load(x1, c1, x2, c2, (long long)n * HW + pix, c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sm[i] += f[i];
+        sq[i] += f[i] * f[i];
+      }
+    }
+    // fold the 8 channels into (at most two) group bins, then one shared atomic per bin
+    int g_prev = c / cpg;
+    float as = 0.f, aq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / cpg;
+      if (g != g_prev) {
+        atomicAdd(&s_sum[g_prev], as);
+        atomicAdd(&s_sq[g_prev], aq);
+        as = aq = 0.f;
+        g_prev = g;
+      }
+      as += sm[i];
+      aq += sq[i];
+    }
+    atomicAdd(&s_sum[g_prev], as);
+    atomicAdd(&s_sq[g_prev], aq);
+  } else {
+    // very wide rows (vecs > blockDim): a thread walks several vectors of each pixel
+    for (long long pix = p0; pix < p1; ++pix) {
+      for (int v = threadIdx.x; v < vecs; v += blockDim.x) {
+        const int c = v * 8;
+        float f[8];
+        unpack8(gn_load(x1, c1, x2, c2, (long long)n * HW + pix, c), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int g = (c + i) / cpg;
+          atomicAdd(&s_sum[g], f[i]);
+          atomicAdd(&s_sq[g], f[i] * f[i]);
+        }
+      }
+    }
   }
   __syncthreads();
   if (threadIdx.x < groups) {
@@ -126,54 +144,63 @@ gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   }
 }
 
-// Pass 2: normalise + affine (+SiLU), write the (possibly concatenated) tensor.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(320)
 gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
                 long long HW, int groups, const __half* __restrict__ gamma,
                 const __half* __restrict__ beta, float eps, int silu,
-                const double* __restrict__ ws, __half* __restrict__ out, long long total_vecs) {
+                const double* __restrict__ ws, __half* __restrict__ out, long long pix_per_cta) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int vecs = C / 8;
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  long long p1 = p0 + pix_per_cta;
+  if (p1 > HW) p1 = HW;
   const double cnt = (double)HW * cpg;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total_vecs;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(it % vecs);
-    const long long pixn = it / vecs;  // n*HW + pix
-    const int n = (int)(pixn / HW);
+  const int lanes = blockDim.x / vecs;
+  const int vstep = lanes >= 1 ? vecs : blockDim.x;
+  const int pstep = lanes >= 1 ? lanes : 1;
+  for (int v = threadIdx.x % vstep; v < vecs; v += vstep) {
     const int c = v * 8;
-    uint4 u;
-    if (c < c1)
-      u = __ldg(reinterpret_cast<const uint4*>(x1 + pixn * c1 + c));
-    else
-      u = __ldg(reinterpret_cast<const uint4*>(x2 + pixn * c2 + (c - c1)));
-    float f[8], g8[8], b8[8];
-    unpack8(u, f);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + c)), g8);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c)), b8);
-    int gprev = -1;
-    float mean = 0.f, rstd = 0.f;
+    float a8[8], b8[8];
+    {
+      float g8[8], be8[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + c)), g8);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c)), be8);
+      int gprev = -1;
+      float mean = 0.f, rstd = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (c + i) / cpg;
-      if (g != gprev) {
-        const double s = ws[((long long)n * groups + g) * 2 + 0];
-        const double q = ws[((long long)n * groups + g) * 2 + 1];
-        const double m = s / cnt;
-        double var = q / cnt - m * m;
-        if (var < 0) var = 0;
-        mean = (float)m;
-        rstd = (float)(1.0 / sqrt(var + (double)eps));
-        gprev = g;
+      for (int i = 0; i < 8; ++i) {
+        const int g = (c + i) / cpg;
+        if (g != gprev) {
+          const double s = ws[((long long)n * groups + g) * 2 + 0];
+          const double q = ws[((long long)n * groups + g) * 2 + 1];
+          const double m = s / cnt;
+          double var = q / cnt - m * m;
+          if (var < 0) var = 0;
+          mean = (float)m;
+          rstd = rsqrtf((float)var + eps);
+          gprev = g;
+        }
+        a8[i] = rstd * g8[i];
+        b8[i] = be8[i] - mean * a8[i];
       }
-      float y = (f[i] - mean) * rstd * g8[i] + b8[i];
-      if (silu) {
-        y = rh(y);  // reference materialises the GroupNorm output in fp16 before SiLU
-        y = y / (1.f + __expf(-y));
-      }
-      f[i] = y;
     }
-    *reinterpret_cast<uint4*>(out + pixn * C + c) = pack8(f);
+    for (long long pix = p0 + (lanes >= 1 ? threadIdx.x / vecs : 0); pix < p1; pix += pstep) {
+      const long long pixn = (long long)n * HW + pix;
+      float f[8];
+      unpack8(gn_load(x1, c1, x2, c2, pixn, c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(f[i], a8[i], b8[i]);
+        if (silu) {
+          y = rh(y);  // reference materialises the GroupNorm output in fp16 before SiLU
+          y = y / (1.f + __expf(-y));
+        }
+        f[i] = y;
+      }
+      *reinterpret_cast<uint4*>(out + pixn * C + c) = pack8(f);
+    }
   }
 }
 
@@ -558,20 +585,23 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* dws = reinterpret_cast<double*>(ws);
   cudaMemsetAsync(dws, 0, sizeof(double) * 2 * NB * groups, st);
-  // enough CTAs to fill the machine: NB * chunks >= ~4 x SMs
-  long long chunks = (4LL * num_sms() + NB - 1) / NB;
+  const int vecs = C / 8;
+  // block = largest multiple of vecs that fits 256 threads (or 320 for C = 2560); wide rows fall back to 256
+  int threads = vecs <= 320 ? (vecs <= 256 ? (256 / vecs) * vecs : vecs) : 256;
+  if (threads < 64) threads = vecs * ((64 + vecs - 1) / vecs);
+  // enough CTAs to fill the machine: NB * chunks >= ~6 x SMs, at least 4 pixels per pixel-lane
+  long long chunks = (6LL * num_sms() + NB - 1) / NB;
   long long ppc = (HW + chunks - 1) / chunks;
-  if (ppc < 8) ppc = 8;
+  const long long min_ppc = 4LL * (threads / vecs > 0 ? threads / vecs : 1);
+  if (ppc < min_ppc) ppc = min_ppc;
   chunks = (HW + ppc - 1) / ppc;
   dim3 grid((unsigned)chunks, (unsigned)NB);
-  gn_stats_kernel<<<grid, GN_THREADS, 0, st>>>(static_cast<const __half*>(x1), c1,
-                                               static_cast<const __half*>(x2), c2, HW, groups, ppc, dws);
+  gn_stats_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2,
+                                            HW, groups, ppc, dws);
   if (int rc = check_launch("gn_stats")) return rc;
-  const long long total_vecs = (long long)NB * HW * (C / 8);
-  gn_apply_kernel<<<grid_for(total_vecs, 256), 256, 0, st>>>(
-      static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, HW, groups,
-      static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps, silu, dws,
-      static_cast<__half*>(out), total_vecs);
+  gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, HW,
+                                            groups, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
+                                            eps, silu, dws, static_cast<__half*>(out), ppc);
   return check_launch("gn_apply");
 }
 
