@@ -177,51 +177,83 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 def gemm_roofline_pass(net, sampler_cls, cond, uncond, batch, L):
-    """Instrumented eager pass over ONE CFG-pair UNet evaluation: CUDA events around every
-    pfd_gemm_f16 launch (the dominant kernel), algorithmic FLOPs from the descriptor
-    (2 * rows * N * K).  Returns (total_flops, total_ms, launches)."""
+    """Device time of the dominant kernel (pfd_gemm_f16 = tcgen05 GEMM / implicit-GEMM conv) inside ONE
+    CFG-pair UNet evaluation, measured live with CUDA events and without host-launch gaps:
+    the evaluation is captured into a CUDA graph twice — once complete, once with every pfd_gemm_f16
+    launch elided — and both graphs are replayed back to back; kernel time = T_full - T_without.
+    Algorithmic FLOPs = sum over launches of 2 * rows * N * K from the call descriptors.
+    Returns (total_flops, gemm_ms, launches, breakdown_ms)."""
     import torch
     from pfd_b200 import native as nv
-    rec = []
-    orig = nv.gemm_raw
-
-    def wrapped(segs, **kw):
-        rows = kw["W"] * kw["H"] * kw["NB"]
-        ktot = sum(taps * c for (_, taps, c, _) in segs)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        orig(segs, **kw)
-        e1.record()
-        rec.append((2.0 * rows * kw["N"] * ktot, e0, e1,
-                    dict(rows=rows, W=kw["W"], H=kw["H"], NB=kw["NB"], N=kw["N"], K=ktot, taps=[t for (_, t, _, _) in segs],
-                         stride=kw["stride"], act=kw.get("act", 0), batched=bool(kw.get("b_batch_stride", 0)))))
-
     c_full = torch.cat([uncond, cond])
     prep = net.prepare_context(c_full, "image")
     x = torch.randn((batch, 4, L, L), device="cuda", dtype=torch.float16)
     t_in = torch.full((2 * batch,), 501, device="cuda", dtype=torch.long)
     c_info = {"type": "image", "c": prep["c"], "_pfd_prepared": prep, "control": None}
-    net.apply_model({"type": "image", "x": torch.cat([x, x])}, t_in, c_info)      # warm
+
+    def run():
+        return net.apply_model({"type": "image", "x": torch.cat([x, x])}, t_in, c_info)
+
+    stats = {"flops": 0.0, "n": 0}
+    orig = {"gemm_raw": nv.gemm_raw, "flash_attn": nv.flash_attn, "groupnorm": nv.groupnorm, "layernorm": nv.layernorm}
+
+    def counting(segs, **kw):
+        stats["flops"] += 2.0 * kw["W"] * kw["H"] * kw["NB"] * kw["N"] * sum(t * c for (_, t, c, _) in segs)
+        stats["n"] += 1
+        orig["gemm_raw"](segs, **kw)
+
+    run()
     torch.cuda.synchronize()
-    nv.gemm_raw = wrapped
+    nv.gemm_raw = counting
     try:
-        net.apply_model({"type": "image", "x": torch.cat([x, x])}, t_in, c_info)
-        torch.cuda.synchronize()
+        run()
     finally:
-        nv.gemm_raw = orig
-    flops = sum(r[0] for r in rec)
-    ms = sum(r[1].elapsed_time(r[2]) for r in rec)
-    dump = os.environ.get("PFD_BENCH_DUMP")
-    if dump:
-        rows = []
-        for fl, a, b, info in rec:
-            t = a.elapsed_time(b)
-            rows.append(dict(info, ms=t, tflops=fl / t / 1e9 if t > 0 else 0.0))
-        rows.sort(key=lambda r: -r["ms"])
-        with open(dump, "w") as f:
-            for r in rows:
-                f.write(json.dumps(r) + "\n")
-    return flops, ms, len(rec)
+        nv.gemm_raw = orig["gemm_raw"]
+    torch.cuda.synchronize()
+
+    def graph_ms(skip=()):
+        saved = {k: getattr(nv, k) for k in skip}
+        try:
+            if "gemm_raw" in skip:
+                nv.gemm_raw = lambda segs, **kw: None
+            if "flash_attn" in skip:
+                nv.flash_attn = lambda q, k, vt, **kw: kw["out"]
+            if "groupnorm" in skip:
+                def gn(x_, g_, b_, eps_, silu=False, x2=None, groups=32, out=None):
+                    if out is not None:
+                        return out
+                    c2 = x2.shape[3] if x2 is not None else 0
+                    return torch.empty(x_.shape[:3] + (x_.shape[3] + c2,), device=x_.device, dtype=torch.float16)
+                nv.groupnorm = gn
+            if "layernorm" in skip:
+                nv.layernorm = lambda x_, g_, b_, eps_=1e-5, residual=None, out=None: (out if out is not None else torch.empty_like(x_))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+        finally:
+            for k, v in saved.items():
+                setattr(nv, k, v)
+        g.replay()
+        torch.cuda.synchronize()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    t_full = graph_ms()
+    t_nogemm = graph_ms(("gemm_raw",))
+    br = {"unet_eval_ms": t_full, "gemm_ms": t_full - t_nogemm}
+    try:
+        br["flash_attn_ms"] = t_full - graph_ms(("flash_attn",))
+        br["groupnorm_ms"] = t_full - graph_ms(("groupnorm",))
+        br["layernorm_ms"] = t_full - graph_ms(("layernorm",))
+    except Exception as e:  # breakdown is informational only
+        br["breakdown_error"] = str(e)
+    return stats["flops"], max(t_full - t_nogemm, 1e-6), stats["n"], br
 
 
 def run_ours(args):
@@ -307,12 +339,14 @@ def run_ours(args):
     if rank == 0:
         peak_t = peaks.get("bf16_tflops_sustained", 1400.0)
         which = "of measured (sustained, MEASURED_PEAKS.json)" if peaks else "of fallback"
-        flops, gms, nl = gemm_roofline_pass(net, DDIMSampler, cond, uncond, B, L)
+        flops, gms, nl, breakdown = gemm_roofline_pass(net, DDIMSampler, cond, uncond, B, L)
         achieved = flops / (gms / 1000.0) / 1e12 if gms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "pfd::gemm_tc_kernel<BN> (tcgen05 GEMM / implicit-GEMM conv)",
                     "achieved": achieved, "peak": peak_t, "unit": "TFLOP/s", "frac": achieved / peak_t,
                     "traffic": None, "peak_source": which, "launches_in_unet_eval": nl,
                     "algorithmic_gflop_in_unet_eval": flops / 1e9, "kernel_ms_in_unet_eval": gms,
+                    "how": "CUDA events around graph replays of one CFG-pair UNet eval, with minus without the kernel's launches",
+                    "unet_eval_breakdown_ms": breakdown,
                     "pipeline_frac": (value / world) * F_IMG_TFLOP / peak_t}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:

@@ -209,23 +209,32 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       mbar_wait(bar_s_full(st), u & 1);
       tc_fence_after();
       const uint32_t tS = tmem_base + lane_off + st * FA_BKV;
-      // pass 1: row max of the fp16 logits (two keys per HMNMX2)
+      // single pass over S (TMEM reads are the scarce resource: 64 B/clk/SM): logits -> packed fp16 in
+      // registers (32 x half2 for 64 keys), running max with HMNMX2
+      __half2 v[FA_BKV / 2];
       __half2 mx2 = ninf2;
-#pragma unroll
-      for (int c = 0; c < FA_BKV / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(tS + c * 16, r);
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tS, r0);
+        tmem_ld32(tS + 32, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          __half2 v = __floats2half2_rn(__uint_as_float(r[i]) * sc, __uint_as_float(r[i + 1]) * sc);
-          if (partial) {
-            if (c * 16 + i >= kvalid) v = ninf2;
-            else if (c * 16 + i + 1 >= kvalid) v = __halves2half2(__low2half(v), __float2half_rn(-INFINITY));
-          }
-          mx2 = __hmax2(mx2, v);
+        for (int i = 0; i < 32; i += 2) {
+          v[i >> 1] = __floats2half2_rn(__uint_as_float(r0[i]) * sc, __uint_as_float(r0[i + 1]) * sc);
+          v[16 + (i >> 1)] = __floats2half2_rn(__uint_as_float(r1[i]) * sc, __uint_as_float(r1[i + 1]) * sc);
         }
       }
+      tc_fence_before();
+      mbar_arrive(bar_s_free(st));                      // S buffer can be overwritten by QK^T of block j+2
+      if (partial) {
+#pragma unroll
+        for (int i = 0; i < FA_BKV / 2; ++i) {
+          if (2 * i >= kvalid) v[i] = ninf2;
+          else if (2 * i + 1 >= kvalid) v[i] = __halves2half2(__low2half(v[i]), __float2half_rn(-INFINITY));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < FA_BKV / 2; ++i) mx2 = __hmax2(mx2, v[i]);
       const float m_new = fmaxf(m, fmaxf(__low2float(mx2), __high2float(mx2)));
       const float alpha = (j == 0) ? 0.f : fast_exp2((m - m_new) * LOG2E);
       const __half2 mh2 = __float2half2_rn(m_new);     // exact: m_new is an fp16 value
@@ -233,29 +242,17 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
         mbar_wait(bar_pv_done, (j - 1) & 1);           // PV_{j-1} finished: P buffer free, O stable
         tc_fence_after();
       }
-      // pass 2: p = 2^((v - m) * log2e) on packed halves -> P tile in shared memory
+      // p = 2^((v - m) * log2e) on packed halves -> P tile in shared memory (swizzled K-major A operand)
 #pragma unroll
-      for (int c = 0; c < FA_BKV / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(tS + c * 16, r);
-        tmem_ld_wait();
-        uint32_t pk[8];
+      for (int g = 0; g < FA_BKV / 8; ++g) {
+        uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          __half2 v = __floats2half2_rn(__uint_as_float(r[i]) * sc, __uint_as_float(r[i + 1]) * sc);
-          if (partial) {
-            if (c * 16 + i >= kvalid) v = ninf2;
-            else if (c * 16 + i + 1 >= kvalid) v = __halves2half2(__low2half(v), __float2half_rn(-INFINITY));
-          }
-          const __half2 t = __hmul2(__hsub2(v, mh2), log2e2);
-          pk[i >> 1] = ex2_f16x2(*reinterpret_cast<const uint32_t*>(&t));
+        for (int i = 0; i < 4; ++i) {
+          const __half2 t = __hmul2(__hsub2(v[g * 4 + i], mh2), log2e2);
+          pk[i] = ex2_f16x2(*reinterpret_cast<const uint32_t*>(&t));
         }
-        const int g0 = c * 2;
-        *reinterpret_cast<uint4*>(prow + (((g0) ^ rsw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(prow + (((g0 + 1) ^ rsw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(prow + ((g ^ rsw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      tc_fence_before();
-      mbar_arrive(bar_s_free(st));
       m = m_new;
       // rescale the running output (and its row-sum column) when this warp's maxima moved
       if (j > 0) {
@@ -279,15 +276,9 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
     // ---- epilogue: O / l -> [B, Nq, heads*d]   (l = column d of the accumulator)
     mbar_wait(bar_pv_done, (nblk - 1) & 1);
     tc_fence_after();
-    float l = 0.f;
-    {
-      uint32_t o[16];
-      tmem_ld16(tmem_O + lane_off + (d & ~15), o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i == (d & 15)) l = __uint_as_float(o[i]);
-    }
+    const uint32_t lraw = tmem_ld1(tmem_O + lane_off + d);
+    tmem_ld_wait();
+    const float l = __uint_as_float(lraw);
     const int q = q0 + row;
     const float inv = l > 0.f ? 1.f / l : 0.f;
     const int b = bh / p.heads, h = bh % p.heads;

@@ -4,7 +4,7 @@
 //
 //   D[128 x BN] (fp32, TMEM)  +=  A[128 x 64] (fp16, smem, TMA 4-D box)  x  B[BN x 64]^T (fp16, smem)
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..5 = epilogue
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2..9 = epilogue
 // (TMEM -> registers -> fused bias / time-embedding / activation / GEGLU / residual -> global).
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of
 // tile i+1.  See include/pfd_b200.h (pfd_gemm_f16) for the reference call sites this replaces.
@@ -23,7 +23,7 @@ namespace pfd {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STAGE_A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int SMEM_BUDGET = 232448;         // 227 KiB opt-in limit per CTA
 
@@ -69,6 +69,16 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == PFD_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
   if (act == PFD_ACT_RELU) return fmaxf(v, 0.f);
   return v;
+}
+
+__device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
 }
 
 __device__ __forceinline__ void load8h(const __half* p, float (&f)[8]) {
@@ -118,7 +128,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 256);
     }
     mbar_fence_init();
   }
@@ -204,15 +214,25 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter, each owning half of the tile's column chunks: the lone-warp-per-
+    // scheduler epilogue was latency-bound (ncu: 214 instr and several exposed load latencies per
+    // 16 columns).  Per chunk all global loads (bias / row add / residual) are issued before the
+    // TMEM load is waited on, index arithmetic is hoisted out of the chunk loop.
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half_id = (warp - 2) >> 2;    // 0: warps 2..5, 1: warps 6..9
     const int row = q * 32 + lane;
     const int rdx = row % p.bw;
     const int rdy = (row / p.bw) % p.bh;
     const int rdn = row / (p.bw * p.bh);
     const bool geglu = (p.act == PFD_ACT_GEGLU);
     const int n_out = geglu ? p.N / 2 : p.N;
-    constexpr int CB = BN;  // columns per tile in TMEM
+    constexpr int CB = BN;                  // accumulator columns per tile in TMEM
+    const int ocols = geglu ? CB / 2 : CB;  // output columns this tile produces
+    const int nch = ocols / 16;
+    const int ch_begin = half_id == 0 ? 0 : (nch + 1) / 2;
+    const int ch_end = half_id == 0 ? (nch + 1) / 2 : nch;
+    const bool plain_cols = p.cdiv >= p.N;  // no head split: column offset = col * so_c0
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -228,58 +248,83 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       const bool valid = (x < p.W) && (y < p.H) && (n < p.NB);
       const long long row_off = (long long)(n / p.ndiv) * p.so_n1 + (long long)(n % p.ndiv) * p.so_n0 +
                                 (long long)y * p.so_y + (long long)x * p.so_x;
+      const int col_base = n_tile * ocols;  // first output column of the tile
+      const __half* rowadd_row = p.rowadd ? p.rowadd + (long long)n * p.rowadd_ld : nullptr;
+      // (head, element) of the first column this warp handles, advanced by 8 per half-chunk
+      int hcol = 0, ecol = col_base + ch_begin * 16;
+      if (!plain_cols) {
+        hcol = ecol / p.cdiv;
+        ecol = ecol % p.cdiv;
+      }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * CB;
-      const int ocols = geglu ? CB / 2 : CB;             // output columns this tile produces
-      const int col_base = n_tile * ocols;               // first output column of the tile
-      for (int c0 = 0; c0 < ocols; c0 += 16) {
-        if (col_base + c0 >= n_out) break;               // warp-uniform
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int c0 = ch * 16;
+        if (col_base + c0 >= n_out) break;  // warp-uniform
         uint32_t r[16];
         uint32_t g[16];
         tmem_ld16(taddr + c0, r);
         if (geglu) tmem_ld16(taddr + CB / 2 + c0, g);
-        tmem_ld_wait();
-        if (valid) {
+        // issue every global load of this chunk before waiting for TMEM
+        uint4 bias_u[2], gate_u[2], radd_u[2], res_u[2];
+        long long coff[2];
+        bool live[2];
 #pragma unroll
         for (int h8 = 0; h8 < 2; ++h8) {
           const int col = col_base + c0 + h8 * 8;
-          if (col >= n_out) break;
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[h8 * 8 + i]) * p.alpha;
-          if (geglu) {
-            float gt[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) gt[i] = __uint_as_float(g[h8 * 8 + i]) * p.alpha;
+          live[h8] = valid && (col < n_out);
+          if (plain_cols) {
+            coff[h8] = (long long)col * p.so_c0;
+          } else {
+            coff[h8] = (long long)hcol * p.so_c1 + (long long)ecol * p.so_c0;
+            ecol += 8;
+            if (ecol >= p.cdiv) {
+              ecol -= p.cdiv;
+              ++hcol;
+            }
+          }
+          bias_u[h8] = gate_u[h8] = radd_u[h8] = res_u[h8] = make_uint4(0, 0, 0, 0);
+          if (col < n_out) {
             if (p.bias) {
-              float bv[8], bg[8];
-              load8h(p.bias + (long long)n_tile * CB + c0 + h8 * 8, bv);
-              load8h(p.bias + (long long)n_tile * CB + CB / 2 + c0 + h8 * 8, bg);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                v[i] += bv[i];
-                gt[i] += bg[i];
+              if (geglu) {
+                bias_u[h8] = __ldg(reinterpret_cast<const uint4*>(p.bias + (long long)n_tile * CB + c0 + h8 * 8));
+                gate_u[h8] = __ldg(reinterpret_cast<const uint4*>(p.bias + (long long)n_tile * CB + CB / 2 + c0 + h8 * 8));
+              } else {
+                bias_u[h8] = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
               }
             }
+            if (live[h8]) {
+              if (rowadd_row) radd_u[h8] = __ldg(reinterpret_cast<const uint4*>(rowadd_row + col));
+              if (p.residual && p.vec_ok) res_u[h8] = __ldg(reinterpret_cast<const uint4*>(p.residual + row_off + coff[h8]));
+            }
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          if (!live[h8]) continue;
+          const int col = col_base + c0 + h8 * 8;
+          float v[8], bv[8];
+          unpack8h(bias_u[h8], bv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaf(__uint_as_float(r[h8 * 8 + i]), p.alpha, bv[i]);
+          if (geglu) {
+            float gt[8], bg[8];
+            unpack8h(gate_u[h8], bg);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
+              gt[i] = fmaf(__uint_as_float(g[h8 * 8 + i]), p.alpha, bg[i]);
               // reference rounds proj output to fp16 before the gate product (attention.py:50-51)
-              float a = __half2float(__float2half_rn(v[i]));
-              float b = __half2float(__float2half_rn(gt[i]));
-              float ge = 0.5f * b * (1.f + erff(b * 0.70710678118654752f));
+              const float a = __half2float(__float2half_rn(v[i]));
+              const float b = __half2float(__float2half_rn(gt[i]));
+              const float ge = 0.5f * b * (1.f + erff(b * 0.70710678118654752f));
               v[i] = a * __half2float(__float2half_rn(ge));
             }
           } else {
-            if (p.bias) {
-              float bv[8];
-              load8h(p.bias + col, bv);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += bv[i];
-            }
-            if (p.rowadd) {
+            if (rowadd_row) {
               float rv[8];
-              load8h(p.rowadd + (long long)n * p.rowadd_ld + col, rv);
+              unpack8h(radd_u[h8], rv);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += rv[i];
             }
@@ -288,11 +333,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
               for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], p.act);
             }
           }
-          const long long coff = (long long)(col / p.cdiv) * p.so_c1 + (long long)(col % p.cdiv) * p.so_c0;
           if (p.vec_ok) {
             if (p.residual) {
               float rv[8];
-              load8h(p.residual + row_off + coff, rv);
+              unpack8h(res_u[h8], rv);
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] += rv[i];
             }
@@ -300,20 +344,21 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            *reinterpret_cast<uint4*>(p.out + row_off + coff) = o;
+            *reinterpret_cast<uint4*>(p.out + row_off + coff[h8]) = o;
           } else {
+            // element-strided output (e.g. transposed V^T): 8 scalar stores
+            const long long estep = p.so_c0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int c = col + i;
-              const long long off =
-                  row_off + (long long)(c / p.cdiv) * p.so_c1 + (long long)(c % p.cdiv) * p.so_c0;
+              // columns of one 8-group never straddle a head boundary (cdiv % 8 == 0 is required)
+              const long long off = row_off + coff[h8] + (long long)i * estep;
               float t = v[i];
               if (p.residual) t += __half2float(p.residual[off]);
               p.out[off] = __float2half_rn(t);
             }
           }
+          (void)col;
         }
-        }  // valid
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
