@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(320)
 gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
                 long long HW, int groups, const __half* __restrict__ gamma,
                 const __half* __restrict__ beta, float eps, int silu,
-                const double* __restrict__ ws, __half* __restrict__ out, long long pix_per_cta) {
+                const double* __restrict__ ws, __half* __restrict__ out, long long pix_per_cta,
+                double inv_cnt) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int vecs = C / 8;
@@ -156,7 +157,6 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   const long long p0 = (long long)blockIdx.x * pix_per_cta;
   long long p1 = p0 + pix_per_cta;
   if (p1 > HW) p1 = HW;
-  const double cnt = (double)HW * cpg;
   const int lanes = blockDim.x / vecs;
   const int vstep = lanes >= 1 ? vecs : blockDim.x;
   const int pstep = lanes >= 1 ? lanes : 1;
@@ -173,10 +173,9 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
       for (int i = 0; i < 8; ++i) {
         const int g = (c + i) / cpg;
         if (g != gprev) {
-          const double s = ws[((long long)n * groups + g) * 2 + 0];
-          const double q = ws[((long long)n * groups + g) * 2 + 1];
-          const double m = s / cnt;
-          double var = q / cnt - m * m;
+          // fp64 only for the cancellation-prone E[x^2] - mean^2 (3 DP ops, no DP division)
+          const double m = ws[((long long)n * groups + g) * 2 + 0] * inv_cnt;
+          double var = ws[((long long)n * groups + g) * 2 + 1] * inv_cnt - m * m;
           if (var < 0) var = 0;
           mean = (float)m;
           rstd = rsqrtf((float)var + eps);
@@ -186,21 +185,30 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
         b8[i] = be8[i] - mean * a8[i];
       }
     }
-    for (long long pix = p0 + (lanes >= 1 ? threadIdx.x / vecs : 0); pix < p1; pix += pstep) {
-      const long long pixn = (long long)n * HW + pix;
+    auto emit = [&](long long pixn, const uint4& u) {
       float f[8];
-      unpack8(gn_load(x1, c1, x2, c2, pixn, c), f);
+      unpack8(u, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float y = fmaf(f[i], a8[i], b8[i]);
         if (silu) {
           y = rh(y);  // reference materialises the GroupNorm output in fp16 before SiLU
-          y = y / (1.f + __expf(-y));
+          y = __fdividef(y, 1.f + __expf(-y));
         }
         f[i] = y;
       }
       *reinterpret_cast<uint4*>(out + pixn * C + c) = pack8(f);
+    };
+    long long pix = p0 + (lanes >= 1 ? threadIdx.x / vecs : 0);
+    const long long base = (long long)n * HW;
+    for (; pix + 3 * pstep < p1; pix += 4 * pstep) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = gn_load(x1, c1, x2, c2, base + pix + k * pstep, c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) emit(base + pix + k * pstep, u[k]);
     }
+    for (; pix < p1; pix += pstep) emit(base + pix, gn_load(x1, c1, x2, c2, base + pix, c));
   }
 }
 
@@ -589,10 +597,10 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   // block = largest multiple of vecs that fits 256 threads (or 320 for C = 2560); wide rows fall back to 256
   int threads = vecs <= 320 ? (vecs <= 256 ? (256 / vecs) * vecs : vecs) : 256;
   if (threads < 64) threads = vecs * ((64 + vecs - 1) / vecs);
-  // enough CTAs to fill the machine: NB * chunks >= ~6 x SMs, at least 4 pixels per pixel-lane
-  long long chunks = (6LL * num_sms() + NB - 1) / NB;
+  // ~3 CTAs per SM, but at least 16 pixels per pixel-lane so the per-CTA setup is amortised
+  long long chunks = (3LL * num_sms() + NB - 1) / NB;
   long long ppc = (HW + chunks - 1) / chunks;
-  const long long min_ppc = 4LL * (threads / vecs > 0 ? threads / vecs : 1);
+  const long long min_ppc = 16LL * (threads / vecs > 0 ? threads / vecs : 1);
   if (ppc < min_ppc) ppc = min_ppc;
   chunks = (HW + ppc - 1) / ppc;
   dim3 grid((unsigned)chunks, (unsigned)NB);
@@ -601,7 +609,8 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   if (int rc = check_launch("gn_stats")) return rc;
   gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, HW,
                                             groups, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
-                                            eps, silu, dws, static_cast<__half*>(out), ppc);
+                                            eps, silu, dws, static_cast<__half*>(out), ppc,
+                                            1.0 / ((double)HW * (C / groups)));
   return check_launch("gn_apply");
 }
 

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import native as nv
+from .graphs import weights_signature
 
 
 def eta_is_zero(sigmas) -> bool:
@@ -30,7 +31,7 @@ class DDIMSampler(object):
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
         self.use_cuda_graph = kwargs.get("use_cuda_graph", True)
-        self._graph = None
+        self._states = {}
 
     def register_buffer(self, name, attr):
         setattr(self, name, attr)
@@ -73,7 +74,10 @@ class DDIMSampler(object):
 
     @torch.no_grad()
     def ddim_sampling(self, shape, x_info, c_info, noise_dropout=0.0, temperature=1.0, log_every_t=100):
-        """ddim.py:81-127."""
+        """ddim.py:81-127.  The per-step work (CFG batch -> UNet [+ControlNet] -> fused CFG combine + DDIM
+        update, in place on a static latent buffer) and the step-invariant preparation (cross-attention
+        K/V of the context, ControlNet hint stem) are captured into CUDA graphs that are cached across
+        calls, keyed on shapes + a signature of the weights they baked in."""
         model = self.model
         device = model.device
         if noise_dropout > 0.0:
@@ -81,68 +85,122 @@ class DDIMSampler(object):
         bs = shape[0]
         timesteps = self.ddim_timesteps
         if x_info.get("xt", None) is not None:
-            x = x_info["xt"].to(device=device, dtype=torch.float16).clone()
+            x_T = x_info["xt"].to(device=device, dtype=torch.float16)
         elif x_info.get("x0", None) is not None:
             raise NotImplementedError("img2img (x0) sampling is outside the pfd_b200 hot path (SURVEY.md §8f)")
         else:
             # same RNG call as ddim.py:105 (dtype of the conditioning; fp16 on the GPU path)
-            x = torch.randn(shape, device=device, dtype=c_info["conditioning"].dtype).to(torch.float16)
-        x_info["x"] = x
+            x_T = torch.randn(shape, device=device, dtype=c_info["conditioning"].dtype).to(torch.float16)
         guidance = float(c_info["unconditional_guidance_scale"])
         cond = c_info["conditioning"]
         uncond = c_info.get("unconditional_conditioning", None)
         use_cfg = not (guidance == 1.0 or uncond is None)
-        c_full = torch.cat([uncond, cond]) if use_cfg else cond          # ddim.py:147
-        prep = model.prepare_context(c_full, c_info["type"])
-        c_info["c"] = prep["c"]
-        c_info["_pfd_prepared"] = prep
-        coef = self._coef_table(device)
-        step_idx = torch.zeros(1, dtype=torch.int32, device=device)
+        c_full = (torch.cat([uncond, cond]) if use_cfg else cond).to(torch.float16).contiguous()   # ddim.py:147
+        cc = c_info.get("control", None)
         total = timesteps.shape[0]
-        intermediates = {"pred_xt": [], "pred_x0": []}
-        pred_x0 = torch.empty_like(x)
         nb = 2 * bs if use_cfg else bs
-        t_in = torch.zeros((nb,), device=device, dtype=torch.long)
-        x = x.contiguous()
+        eta0 = eta_is_zero(self.ddim_sigmas)
 
-        def one_step():
-            # CFG batch (ddim.py:145-150) -> UNet (+ControlNet) -> fused CFG combine + DDIM update, in place on x
-            x_info["x"] = torch.cat([x, x]) if use_cfg else x
-            eps = model.apply_model(x_info, t_in, c_info)
-            if not use_cfg:                                              # e_t = eps * scale (ddim.py:143-144)
-                eps = torch.cat([torch.zeros_like(eps), eps])
-            nv.ddim_step(eps, x, guidance, coef, step_idx, x, pred_x0)
-
-        graph = None
-        use_graph = self.use_cuda_graph and eta_is_zero(self.ddim_sigmas) and total > 2
+        key = (tuple(x_T.shape), tuple(c_full.shape), use_cfg, guidance, c_info["type"], x_info["type"],
+               None if cc is None else (tuple(cc.shape), cc.dtype), total, weights_signature(model))
+        st = self._states.get(key) if self.use_cuda_graph else None
+        if st is None:
+            st = _SamplerState(model, x_T, c_full, cc, nb, total, use_cfg, guidance, x_info["type"], c_info["type"],
+                               capture=self.use_cuda_graph and eta0 and total > 1)
+            if self.use_cuda_graph:
+                if len(self._states) >= 2:
+                    self._states.pop(next(iter(self._states)))
+                self._states[key] = st
+        st.load_request(x_T, c_full, cc, self._coef_table(device))
+        x = st.x
+        intermediates = {"pred_xt": [], "pred_x0": []}
         for i, step in enumerate(np.flip(timesteps)):
             index = total - i - 1
-            t_in.fill_(int(step))
-            step_idx.fill_(index)
-            if use_graph and i == 1:
-                # step 0 ran eagerly (it also built every packed-weight / hint cache); capture the
-                # identical launch sequence once and replay it for the remaining steps.
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                n_before = nv.launch_count()
-                with torch.cuda.graph(graph):
-                    one_step()
-                n_nodes = nv.launch_count() - n_before
-            if graph is not None:
-                graph.replay()
-                nv.note_replay(n_nodes)
-            else:
-                one_step()
+            st.t_in.fill_(int(step))
+            st.step_idx.fill_(index)
+            st.step()
             sigma = float(self.ddim_sigmas[index])
             if sigma != 0.0:
                 noise = torch.randn_like(x)
                 nv.axpby(x, 1.0, noise, sigma * temperature, out=x)
-            x_info["x"] = x
             if index % log_every_t == 0 or index == total - 1:
                 intermediates["pred_xt"].append(x.clone())
-                intermediates["pred_x0"].append(pred_x0.clone())
-        if graph is not None:
+                intermediates["pred_x0"].append(st.pred_x0.clone())
+        out = x.clone()
+        x_info["x"] = out
+        c_info["c"] = c_full
+        return out, intermediates
+
+
+class _SamplerState:
+    """Static buffers + captured graphs of one sampling configuration."""
+
+    def __init__(self, model, x_T, c_full, cc, nb, total, use_cfg, guidance, x_type, c_type, capture):
+        dev = x_T.device
+        self.model, self.use_cfg, self.guidance = model, use_cfg, guidance
+        self.x = torch.empty_like(x_T)
+        self.pred_x0 = torch.empty_like(x_T)
+        self.c = torch.empty_like(c_full)
+        self.cc = None if cc is None else torch.empty_like(cc)
+        self.t_in = torch.zeros((nb,), device=dev, dtype=torch.long)
+        self.step_idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.coef = torch.zeros((total, 4), dtype=torch.float32, device=dev)
+        self.x_info = {"type": x_type}
+        self.c_info = {"type": c_type, "control": self.cc}
+        self.prep_graph = self.step_graph = None
+        self.n_prep = self.n_step = 0
+        # eager pass first: builds every packed-weight cache and validates the launch sequence
+        self.x.copy_(x_T)
+        self.c.copy_(c_full)
+        if cc is not None:
+            self.cc.copy_(cc)
+        self._prepare()
+        if capture:
+            self.t_in.fill_(1)
+            self._one_step()                       # warm-up on scratch state (x is re-loaded per request)
             torch.cuda.synchronize()
-            del graph
-        c_info.pop("_pfd_prepared", None)
-        return x, intermediates
+            self.prep_graph = torch.cuda.CUDAGraph()
+            n0 = nv.launch_count()
+            with torch.cuda.graph(self.prep_graph):
+                self._prepare()
+            self.n_prep = nv.launch_count() - n0
+            self.step_graph = torch.cuda.CUDAGraph()
+            n0 = nv.launch_count()
+            with torch.cuda.graph(self.step_graph):
+                self._one_step()
+            self.n_step = nv.launch_count() - n0
+
+    def _prepare(self):
+        prep = self.model.prepare_context(self.c, self.c_info["type"])
+        if self.cc is not None and hasattr(self.model, "ctl"):
+            prep["hint"] = self.model.ctl.hint_features(self.cc)
+        self.c_info["c"] = prep["c"]
+        self.c_info["_pfd_prepared"] = prep
+
+    def _one_step(self):
+        # CFG batch (ddim.py:145-150) -> UNet (+ControlNet) -> fused CFG combine + DDIM update, in place on x
+        x = self.x
+        self.x_info["x"] = torch.cat([x, x]) if self.use_cfg else x
+        eps = self.model.apply_model(self.x_info, self.t_in, self.c_info)
+        if not self.use_cfg:                                             # e_t = eps * scale (ddim.py:143-144)
+            eps = torch.cat([torch.zeros_like(eps), eps])
+        nv.ddim_step(eps, x, self.guidance, self.coef, self.step_idx, x, self.pred_x0)
+
+    def load_request(self, x_T, c_full, cc, coef):
+        self.x.copy_(x_T)
+        self.c.copy_(c_full)
+        if cc is not None:
+            self.cc.copy_(cc)
+        self.coef.copy_(coef)
+        if self.prep_graph is not None:
+            self.prep_graph.replay()
+            nv.note_replay(self.n_prep)
+        else:
+            self._prepare()
+
+    def step(self):
+        if self.step_graph is not None:
+            self.step_graph.replay()
+            nv.note_replay(self.n_step)
+        else:
+            self._one_step()

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import native as nv
+from .graphs import GraphCache, GraphedFunction, weights_signature
 from .registry import get_model
 
 
@@ -46,6 +47,8 @@ class PromptFreeDiffusion(nn.Module):
         for n, d in self.diffuser.items():
             self.parameter_group.update({f"diffuser_{n}_{k}": v for k, v in d.parameter_group.items()})
         self._hint_cache = None
+        self.use_cuda_graphs = True          # replay captured graphs for ctx_encode / vae_decode (see graphs.py)
+        self._graphs = GraphCache(max_entries=6)
 
     def to(self, device):
         self.device = device
@@ -89,7 +92,14 @@ class PromptFreeDiffusion(nn.Module):
     def vae_decode(self, z, which, **kwargs):
         """pfd.py:275-282: z / scale -> AutoencoderKL.decode -> [B,3,H,W] in [0,1]."""
         scale = self.latent_scale_factor.get(which, None) if self.latent_scale_factor is not None else None
-        return self.vae[which].decode(z, pre_scale=(1.0 / scale) if scale is not None else 1.0, **kwargs)
+        pre = (1.0 / scale) if scale is not None else 1.0
+        vae = self.vae[which]
+        if not (self.use_cuda_graphs and z.is_cuda) or kwargs:
+            return vae.decode(z, pre_scale=pre, **kwargs)
+        z = z.to(torch.float16)
+        key = ("vae", which, tuple(z.shape), pre, weights_signature(vae.decoder, vae.post_quant_conv))
+        gf, hit = self._graphs.get(key, lambda: GraphedFunction(lambda t: vae.decode(t, pre_scale=pre), [z]))
+        return (gf(z) if hit else gf.first_out).clone()
 
     @torch.no_grad()
     def vae_encode(self, x, which, **kwargs):
@@ -100,7 +110,14 @@ class PromptFreeDiffusion(nn.Module):
         """pfd.py:284-289."""
         if which.find("vae_") == 0:
             raise NotImplementedError("vae_* context encoders are outside the pfd_b200 hot path")
-        return self.ctx[which].encode(x, **kwargs)
+        enc = self.ctx[which]
+        if not (self.use_cuda_graphs and x.is_cuda) or kwargs:
+            return enc.encode(x, **kwargs)
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.to(torch.float16)
+        key = ("ctx", which, tuple(x.shape), x.dtype, weights_signature(enc))
+        gf, hit = self._graphs.get(key, lambda: GraphedFunction(lambda t: enc.encode(t), [x]))
+        return (gf(x) if hit else gf.first_out).clone()
 
     def check_diffuser(self):
         orders = [d.layer_order for d in self.diffuser.values()]
@@ -161,7 +178,9 @@ class PromptFreeDiffusion_with_control(PromptFreeDiffusion):
             prep = None
         control = None
         if cc is not None:
+            hint_feat = prep.get("hint") if prep is not None else None
             control = self.ctl(x, hint=cc, timesteps=timesteps, context=c,
-                               kv=prep["ctl"] if prep is not None else None, hint_feat=self._hint(cc))
+                               kv=prep["ctl"] if prep is not None else None,
+                               hint_feat=hint_feat if hint_feat is not None else self._hint(cc))
         return self.diffuser[x_type].apply(x, timesteps, c, control=control,
                                            kv=prep["unet"] if prep is not None else None)

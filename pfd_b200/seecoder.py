@@ -166,9 +166,9 @@ class PPE_MLP(nn.Module):
         h, w = x_hw
         minlen = min(h, w)
         dt = torch.float16
-        he, we = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
-        he = ((he + 0.5 - h / 2) / minlen * (2 * math.pi)).to(device).to(dt)
-        we = ((we + 0.5 - w / 2) / minlen * (2 * math.pi)).to(device).to(dt)
+        he, we = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")
+        he = ((he + 0.5 - h / 2) / minlen * (2 * math.pi)).to(dt)
+        we = ((we + 0.5 - w / 2) / minlen * (2 * math.pi)).to(dt)
         dim_t = torch.linspace(0, 1, self.freq_num, dtype=torch.float32, device=device)
         fmax = self.freq_max if self.freq_max is not None else minlen / 2
         dim_t = fmax ** dim_t.to(dt)
