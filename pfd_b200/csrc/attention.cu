@@ -57,8 +57,9 @@ struct FlashCfg {
   static constexpr int K_BYTES = DCH * FA_BKV * 128;
   static constexpr int DN = DCH == 1 ? 80 : (DCH == 2 ? 144 : 208);  // max rows of the V^T tile (d + ones row, padded)
   static constexpr int P_BYTES = FA_BQ * 128;
+  static constexpr int NPB = DCH == 1 ? 2 : 1;   // P buffers: double-buffered when smem allows 2 CTAs/SM anyway
   // V^T stage = dN rows x 128 B (dN = ceil16(d + 1), runtime) so d=80 still fits two CTAs per SM
-  static int smem_bytes(int dN) { return Q_BYTES + 2 * (K_BYTES + dN * 128) + P_BYTES + 1024 + 128; }
+  static int smem_bytes(int dN) { return Q_BYTES + 2 * (K_BYTES + dN * 128) + NPB * P_BYTES + 1024 + 128; }
 };
 
 template <int DCH>
@@ -77,7 +78,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   const uint32_t sK = sQ + Cfg::Q_BYTES;                  // [2][K_BYTES]
   const uint32_t sV = sK + 2 * Cfg::K_BYTES;              // [2][V_BYTES]
   const uint32_t sP = sV + 2 * V_BYTES;
-  const uint32_t bars = sP + Cfg::P_BYTES;
+  const uint32_t bars = sP + Cfg::NPB * Cfg::P_BYTES;
   uint8_t* gP = gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES;
   const uint32_t bar_q = bars;
   auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
@@ -88,7 +89,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   const uint32_t bar_pv_done = bars + 8u * 10;
   const uint32_t tmem_slot = bars + 8u * 11;
   volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(
-      gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES + Cfg::P_BYTES + 8 * 11);
+      gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES + Cfg::NPB * Cfg::P_BYTES + 8 * 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,7 +182,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
         mbar_wait(bar_p_ready, j & 1);
         tc_fence_after();
         const int st = j & 1;
-        const uint64_t ad = make_sw128_kmajor_desc(sP);
+        const uint64_t ad = make_sw128_kmajor_desc(sP + (Cfg::NPB == 2 ? (j & 1) * Cfg::P_BYTES : 0));
         const uint64_t bd = make_sw128_kmajor_desc(sV + st * V_BYTES);
 #pragma unroll
         for (int s = 0; s < FA_BKV / 16; ++s)
@@ -200,7 +201,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
     const __half2 log2e2 = __float2half2_rn(LOG2E);
     const __half2 ninf2 = __float2half2_rn(-INFINITY);
     float m = -INFINITY;
-    uint8_t* prow = gP + row * 128;
+    uint8_t* prow0 = gP + row * 128;
     const int rsw = row & 7;
     for (int j = 0; j < nblk; ++j) {
       const int st = j & 1, u = j >> 1;
@@ -238,10 +239,11 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       const float m_new = fmaxf(m, fmaxf(__low2float(mx2), __high2float(mx2)));
       const float alpha = (j == 0) ? 0.f : fast_exp2((m - m_new) * LOG2E);
       const __half2 mh2 = __float2half2_rn(m_new);     // exact: m_new is an fp16 value
-      if (j > 0) {
-        mbar_wait(bar_pv_done, (j - 1) & 1);           // PV_{j-1} finished: P buffer free, O stable
+      if (Cfg::NPB == 1 && j > 0) {
+        mbar_wait(bar_pv_done, (j - 1) & 1);           // single P buffer: PV_{j-1} must have consumed it
         tc_fence_after();
       }
+      uint8_t* prow = prow0 + (Cfg::NPB == 2 ? (j & 1) * Cfg::P_BYTES : 0);
       // p = 2^((v - m) * log2e) on packed halves -> P tile in shared memory (swizzled K-major A operand)
 #pragma unroll
       for (int g = 0; g < FA_BKV / 8; ++g) {
@@ -254,6 +256,12 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
         *reinterpret_cast<uint4*>(prow + ((g ^ rsw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       m = m_new;
+      if (Cfg::NPB == 2 && j > 0) {
+        // double-buffered P: exp/write of this block overlapped PV_{j-1}; O must be stable before the
+        // rescale below and before PV_j accumulates into it (also frees P[(j+1)&1] for the next block)
+        mbar_wait(bar_pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
       // rescale the running output (and its row-sum column) when this warp's maxima moved
       if (j > 0) {
         const bool need = __any_sync(0xffffffffu, alpha != 1.f);

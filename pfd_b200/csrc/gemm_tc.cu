@@ -64,9 +64,23 @@ struct GemmCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
 };
 
+// erf to ~1.5e-7 absolute (Abramowitz & Stegun 7.1.26) with MUFU rcp/ex2: about half the
+// instructions of erff(), far below the fp16 output resolution of the GELU / GEGLU epilogues.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float y = 1.f - poly * __expf(-ax * ax);
+  return copysignf(y, x);
+}
+
 __device__ __forceinline__ float act_apply(float v, int act) {
-  if (act == PFD_ACT_SILU) return v / (1.f + __expf(-v));
-  if (act == PFD_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (act == PFD_ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
+  if (act == PFD_ACT_GELU) return 0.5f * v * (1.f + fast_erf(v * 0.70710678118654752f));
   if (act == PFD_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
@@ -318,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
               // reference rounds proj output to fp16 before the gate product (attention.py:50-51)
               const float a = __half2float(__float2half_rn(v[i]));
               const float b = __half2float(__float2half_rn(gt[i]));
-              const float ge = 0.5f * b * (1.f + erff(b * 0.70710678118654752f));
+              const float ge = 0.5f * b * (1.f + fast_erf(b * 0.70710678118654752f));
               v[i] = a * __half2float(__float2half_rn(ge));
             }
           } else {
