@@ -57,7 +57,10 @@ struct FlashCfg {
   static constexpr int K_BYTES = DCH * FA_BKV * 128;
   static constexpr int DN = DCH == 1 ? 80 : (DCH == 2 ? 144 : 208);  // max rows of the V^T tile (d + ones row, padded)
   static constexpr int P_BYTES = FA_BQ * 128;
-  static constexpr int NPB = DCH == 1 ? 2 : 1;   // P buffers: double-buffered when smem allows 2 CTAs/SM anyway
+  static constexpr int NPB = 1;                  // P buffers
+  // S accumulators in TMEM: one for d <= 64 (64 + 48 columns -> 128-column allocation, ~60 KB smem ->
+  // three CTAs per SM overlap each other's TMEM-load / MUFU / smem / MMA phases), two otherwise
+  static constexpr int NSB = DCH == 1 ? 1 : 2;
   // V^T stage = dN rows x 128 B (dN = ceil16(d + 1), runtime) so d=80 still fits two CTAs per SM
   static int smem_bytes(int dN) { return Q_BYTES + 2 * (K_BYTES + dN * 128) + NPB * P_BYTES + 1024 + 128; }
 };
@@ -73,7 +76,8 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   const int d = p.d;
   const int dN = (d + 16) & ~15;       // PV MMA N: d value rows + the all-ones row (-> row sums), padded to 16
   const int V_BYTES = dN * 128;
-  const uint32_t tmem_cols = (128 + dN <= 256) ? 256u : 512u;
+  const uint32_t need_cols = Cfg::NSB * FA_BKV + dN;
+  const uint32_t tmem_cols = need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u);
   const uint32_t sQ = base;
   const uint32_t sK = sQ + Cfg::Q_BYTES;                  // [2][K_BYTES]
   const uint32_t sV = sK + 2 * Cfg::K_BYTES;              // [2][V_BYTES]
@@ -131,7 +135,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
-  const uint32_t tmem_O = tmem_base + 128;
+  const uint32_t tmem_O = tmem_base + Cfg::NSB * FA_BKV;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -152,7 +156,8 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       const uint32_t idesc_o = make_idesc_f16((uint32_t)dN);
       auto issue_S = [&](int j) {
         const int st = j & 1;
-        const uint32_t tS = tmem_base + st * FA_BKV;
+        const int sb = j % Cfg::NSB;
+        const uint32_t tS = tmem_base + sb * FA_BKV;
         bool first = true;
         for (int c = 0; c < DCH; ++c) {
           const int rem = d - c * 64;
@@ -165,7 +170,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
             first = false;
           }
         }
-        umma_commit(bar_s_full(st));
+        umma_commit(bar_s_full(sb));
       };
       mbar_wait(bar_q, 0);
       mbar_wait(bar_kv_full(0), 0);
@@ -174,8 +179,9 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) {
           const int st = (j + 1) & 1, u = (j + 1) >> 1;
+          const int sb = (j + 1) % Cfg::NSB, us = (j + 1) / Cfg::NSB;
           mbar_wait(bar_kv_full(st), u & 1);
-          if (u >= 1) mbar_wait(bar_s_free(st), (u - 1) & 1);
+          if (us >= 1) mbar_wait(bar_s_free(sb), (us - 1) & 1);
           tc_fence_after();
           issue_S(j + 1);
         }
@@ -204,12 +210,12 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
     uint8_t* prow0 = gP + row * 128;
     const int rsw = row & 7;
     for (int j = 0; j < nblk; ++j) {
-      const int st = j & 1, u = j >> 1;
+      const int sb = j % Cfg::NSB, us = j / Cfg::NSB;
       const int kvalid = min(FA_BKV, p.Nk - j * FA_BKV);
       const bool partial = kvalid < FA_BKV;            // block-uniform
-      mbar_wait(bar_s_full(st), u & 1);
+      mbar_wait(bar_s_full(sb), us & 1);
       tc_fence_after();
-      const uint32_t tS = tmem_base + lane_off + st * FA_BKV;
+      const uint32_t tS = tmem_base + lane_off + sb * FA_BKV;
       // single pass over S (TMEM reads are the scarce resource: 64 B/clk/SM): logits -> packed fp16 in
       // registers (32 x half2 for 64 keys), running max with HMNMX2
       __half2 v[FA_BKV / 2];
@@ -226,7 +232,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_s_free(st));                      // S buffer can be overwritten by QK^T of block j+2
+      mbar_arrive(bar_s_free(sb));                      // S buffer may now be overwritten by the next QK^T
       if (partial) {
 #pragma unroll
         for (int i = 0; i < FA_BKV / 2; ++i) {

@@ -14,6 +14,9 @@
 #include <math.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+
 #include "../../include/pfd_b200.h"
 #include "common.h"
 #include "ptx.cuh"
@@ -40,6 +43,9 @@ struct alignas(64) GemmParams {
   int W, H, NB, N;
   int b_batched;
   int num_kb;
+  int splits;        // split-K factor (1 = off); work items = tiles * splits
+  int kb_per_split;
+  float* ws;         // fp32 partials [splits][m_tiles*128][N] when splits > 1
   float alpha;
   int act;
   const __half* bias;
@@ -156,13 +162,18 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_nb;
   const int total_tiles = m_tiles * p.n_tiles;
+  const int total_work = total_tiles * p.splits;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work % total_tiles;
+        const int split = work / total_tiles;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int tx = m_tile % p.tiles_w;
@@ -173,12 +184,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         const int n0 = tn * p.bn;
         const int bcoord = p.b_batched ? n0 : 0;
         int kofs = 0;
+        int kbi = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const int ntap = p.taps[s];
           for (int t = 0; t < ntap; ++t) {
             const int dy = (ntap == 9) ? (t / 3 - 1) : 0;
             const int dx = (ntap == 9) ? (t % 3 - 1) : 0;
-            for (int j = 0; j < p.chunks[s]; ++j) {
+            for (int j = 0; j < p.chunks[s]; ++j, ++kbi) {
+              if (kbi < kb_begin || kbi >= kb_end) continue;
               mbar_wait(empty_bar(stage), phase ^ 1u);
               mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
               tma_load_4d(smemA + stage * STAGE_A_BYTES, &p.tmA[s], full_bar(stage), j * BK,
@@ -202,13 +215,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
+        const int kb_begin = (work / total_tiles) * p.kb_per_split;
+        const int nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(smemA + stage * STAGE_A_BYTES);
@@ -248,7 +263,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const int ch_end = half_id == 0 ? (nch + 1) / 2 : nch;
     const bool plain_cols = p.cdiv >= p.N;  // no head split: column offset = col * so_c0
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+      const int tile = work % total_tiles;
+      const int split = work / total_tiles;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int n_tile = tile % p.n_tiles;
@@ -273,6 +290,26 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * CB;
+      if (p.splits > 1) {
+        // split-K: raw fp32 partials -> workspace; bias/activation/residual happen in splitk_finish_kernel
+        float* wrow = p.ws + ((long long)split * m_tiles * BM + (long long)m_tile * BM + row) * p.N;
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int c0 = ch * 16;
+          if (col_base + c0 >= n_out) break;
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            const int col = col_base + c0 + v4 * 4;
+            if (col < n_out)
+              *reinterpret_cast<uint4*>(wrow + col) = make_uint4(r[v4 * 4], r[v4 * 4 + 1], r[v4 * 4 + 2], r[v4 * 4 + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
       for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int c0 = ch * 16;
         if (col_base + c0 >= n_out) break;  // warp-uniform
@@ -387,7 +424,99 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   }
 }
 
+// Split-K second pass: sum the fp32 partials of all splits and apply the fused epilogue
+// (bias, per-image row add, activation, residual) with the same generic output addressing.
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const __grid_constant__ GemmParams p) {
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_nb;
+  const long long rows_pad = (long long)m_tiles * BM;
+  const int vecs = p.N / 8;
+  const long long total = rows_pad * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vecs);
+    const long long prow = i / vecs;
+    const int m_tile = (int)(prow / BM), row = (int)(prow % BM);
+    const int tx = m_tile % p.tiles_w;
+    const int ty = (m_tile / p.tiles_w) % p.tiles_h;
+    const int tn = m_tile / (p.tiles_w * p.tiles_h);
+    const int x = tx * p.bw + row % p.bw;
+    const int y = ty * p.bh + (row / p.bw) % p.bh;
+    const int n = tn * p.bn + row / (p.bw * p.bh);
+    if (x >= p.W || y >= p.H || n >= p.NB) continue;
+    const int col = v * 8;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(p.ws + ((long long)s * rows_pad + prow) * p.N + col);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    float bv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bv[k] = 0.f;
+    if (p.bias) load8h(p.bias + col, bv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fmaf(acc[k], p.alpha, bv[k]);
+    if (p.rowadd) {
+      float rv[8];
+      load8h(p.rowadd + (long long)n * p.rowadd_ld + col, rv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += rv[k];
+    }
+    if (p.act != PFD_ACT_NONE) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = act_apply(acc[k], p.act);
+    }
+    const long long row_off = (long long)(n / p.ndiv) * p.so_n1 + (long long)(n % p.ndiv) * p.so_n0 +
+                              (long long)y * p.so_y + (long long)x * p.so_x;
+    const long long coff = (long long)(col / p.cdiv) * p.so_c1 + (long long)(col % p.cdiv) * p.so_c0;
+    if (p.vec_ok) {
+      if (p.residual) {
+        float rv[8];
+        load8h(p.residual + row_off + coff, rv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += rv[k];
+      }
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+      *reinterpret_cast<uint4*>(p.out + row_off + coff) = o;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long off = row_off + coff + (long long)k * p.so_c0;
+        float t = acc[k];
+        if (p.residual) t += __half2float(p.residual[off]);
+        p.out[off] = __float2half_rn(t);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
+constexpr size_t SPLITK_WS_BYTES = 64ull << 20;
+static float* splitk_workspace(cudaStream_t st) {
+  // one workspace per stream (calls on distinct streams may run concurrently); allocated on first use,
+  // which happens in the eager warm-up pass that precedes any CUDA-graph capture.
+  static std::mutex mu;
+  static std::map<cudaStream_t, float*> ws;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = ws.find(st);
+  if (it != ws.end()) return it->second;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return nullptr;
+  float* pnew = nullptr;
+  if (cudaMalloc(&pnew, SPLITK_WS_BYTES) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  ws[st] = pnew;
+  return pnew;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -534,6 +663,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   }
   if (best_cost < 0) return set_error("pfd_gemm_f16: no valid N tile (bn_force=%d, N=%d, geglu=%d)", d->bn_force, d->N, (int)geglu);
   p.n_tiles = (int)cdivll(d->N, BNsel);
+  p.splits = 1;
 
   // ---- tensor maps
   int num_kb = 0;
@@ -549,6 +679,38 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
     if (int rc = encode_map(&p.tmA[s], d->a_ptr[s], 4, dims, strides, box, estr, "A")) return rc;
   }
   p.num_kb = num_kb;
+  p.kb_per_split = num_kb;
+  cudaStream_t st = static_cast<cudaStream_t>(d->stream);
+  // ---- split-K for long-K problems that cannot fill the machine (8x8-level convs): fewer, wider N tiles
+  //      (less A re-read through L2) x several K slices, fp32 partials reduced by splitk_finish_kernel.
+  if (!geglu && !d->bn_force && num_kb >= 32) {
+    int bn_sk = 128;
+    const int sk_cands[4] = {256, 192, 160, 128};
+    for (int i = 0; i < 4; ++i)
+      if (d->N % sk_cands[i] == 0) {
+        bn_sk = sk_cands[i];
+        break;
+      }
+    const long long nt_sk = cdivll(d->N, bn_sk);
+    const long long tiles_sk = m_tiles * nt_sk;
+    if (tiles_sk * 2 <= sms) {
+      int splits = (int)(sms / tiles_sk);
+      if (splits > 8) splits = 8;
+      if (splits > num_kb / 8) splits = num_kb / 8;
+      const size_t need = (size_t)splits * (size_t)m_tiles * BM * (size_t)d->N * sizeof(float);
+      if (splits >= 2 && need <= SPLITK_WS_BYTES) {
+        float* ws = splitk_workspace(st);
+        if (ws) {
+          BNsel = bn_sk;
+          p.n_tiles = (int)nt_sk;
+          p.splits = splits;
+          p.kb_per_split = (num_kb + splits - 1) / splits;
+          p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+          p.ws = ws;
+        }
+      }
+    }
+  }
   {
     const long long nbatch = p.b_batched ? d->NB : 1;
     cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)nbatch};
@@ -559,14 +721,20 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
     if (int rc = encode_map(&p.tmB, d->b_ptr, 3, dims, strides, box, estr, "B")) return rc;
   }
 
-  const long long total = m_tiles * p.n_tiles;
+  const long long total = m_tiles * p.n_tiles * p.splits;
   const int grid = (int)(total < sms ? total : sms);
-  cudaStream_t st = static_cast<cudaStream_t>(d->stream);
+  int rc;
   switch (BNsel) {
-    case 64: return launch_gemm<64>(p, grid, st);
-    case 128: return launch_gemm<128>(p, grid, st);
-    case 160: return launch_gemm<160>(p, grid, st);
-    case 192: return launch_gemm<192>(p, grid, st);
-    default: return launch_gemm<256>(p, grid, st);
+    case 64: rc = launch_gemm<64>(p, grid, st); break;
+    case 128: rc = launch_gemm<128>(p, grid, st); break;
+    case 160: rc = launch_gemm<160>(p, grid, st); break;
+    case 192: rc = launch_gemm<192>(p, grid, st); break;
+    default: rc = launch_gemm<256>(p, grid, st); break;
   }
+  if (rc || p.splits == 1) return rc;
+  const long long vec_items = m_tiles * BM * (long long)(d->N / 8);
+  long long fgrid = (vec_items + 255) / 256;
+  if (fgrid > 8LL * sms) fgrid = 8LL * sms;
+  splitk_finish_kernel<<<(unsigned)fgrid, 256, 0, st>>>(p);
+  return check_launch("pfd_gemm_f16(split-K finish)");
 }

@@ -34,7 +34,8 @@ def close(out, ref, rtol=4e-3, atol=4e-3):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 320, 320), (4096, 320, 320), (1000, 1280, 768),
-                                   (77, 640, 1280), (512, 24, 40), (300, 2560, 320), (8, 1280, 1280)])
+                                   (77, 640, 1280), (512, 24, 40), (300, 2560, 320), (8, 1280, 1280),
+                                   (512, 1280, 5120), (100, 640, 4096)])                 # last two: split-K path
 def test_linear(nv, M, N, K):
     x = rnd(M, K, scale=1.0)
     w = rnd(N, K, scale=K ** -0.5, seed=1)
@@ -80,6 +81,7 @@ def test_geglu(nv, C):
 
 
 @pytest.mark.parametrize("NB,H,W,C,N", [(2, 64, 64, 320, 320), (3, 8, 8, 128, 64), (2, 32, 32, 640, 320),
+                                        (8, 8, 8, 1280, 1280), (2, 8, 8, 2560, 1280),   # split-K path
                                         (1, 16, 16, 1280, 640), (2, 24, 24, 64, 128), (1, 12, 12, 64, 64),
                                         (1, 128, 128, 128, 128)])
 def test_conv3x3(nv, NB, H, W, C, N):
