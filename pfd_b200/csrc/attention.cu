@@ -136,6 +136,8 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
   const uint32_t tmem_O = tmem_base + Cfg::NSB * FA_BKV;
+  pdl_wait();                  // q / k / v are produced by the preceding projection GEMMs
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -367,7 +369,7 @@ static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t st) {
     done = true;
   }
   const int smem = Cfg::smem_bytes((p.d + 16) & ~15);
-  flash_attn_kernel<DCH><<<grid, FA_THREADS, smem, st>>>(p);
+  launch_k(flash_attn_kernel<DCH>, grid, dim3(FA_THREADS), (size_t)smem, st, p);
   return check_launch("pfd_flash_attn_f16");
 }
 

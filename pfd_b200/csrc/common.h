@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <string>
@@ -22,6 +23,34 @@ inline int check_launch(const char* what) {
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// Programmatic dependent launch: every pfd kernel begins with griddepcontrol.wait (see pdl_wait() in
+// ptx.cuh / elementwise.cu) so its CTAs may be scheduled while the previous kernel of the stream drains;
+// set PFD_NO_PDL=1 to launch with plain stream ordering.
+inline bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PFD_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 inline int num_sms() {

@@ -12,6 +12,13 @@
 
 namespace pfd {
 
+__device__ __forceinline__ void pdl_enter() {
+  // programmatic dependent launch: block until the producer kernel has completed, then let the
+  // consumer kernel start scheduling its CTAs (see common.h: launch_k)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -58,6 +65,7 @@ __device__ __forceinline__ uint4 gn_load(const __half* __restrict__ x1, int c1, 
 __global__ void __launch_bounds__(320)
 gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
                 long long HW, int groups, long long pix_per_cta, double* __restrict__ ws) {
+  pdl_enter();
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int vecs = C / 8;
@@ -150,6 +158,7 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
                 const __half* __restrict__ beta, float eps, int silu,
                 const double* __restrict__ ws, __half* __restrict__ out, long long pix_per_cta,
                 double inv_cnt) {
+  pdl_enter();
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int vecs = C / 8;
@@ -219,6 +228,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ res, long long rows, int C,
                  const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
                  __half* __restrict__ out) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -276,6 +286,7 @@ __global__ void __launch_bounds__(256)
 softmax_rows_kernel(__half* __restrict__ s, long long batch, int rows, int cols, long long ld,
                     float scale, const __half* __restrict__ bias, int nheads,
                     const __half* __restrict__ mask, int nwin) {
+  pdl_enter();
   // CTA per row, threads stride over columns; values cached in shared memory as fp32.
   extern __shared__ float sv[];
   const long long r = blockIdx.x;  // global row = b*rows + i
@@ -327,6 +338,7 @@ softmax_rows_kernel(__half* __restrict__ s, long long batch, int rows, int cols,
 // ------------------------------------------------------------------------------------ misc
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n, int dim,
                                           float max_period, __half* __restrict__ out) {
+  pdl_enter();
   const int half_d = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * half_d) return;
@@ -341,6 +353,7 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int n
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, int NB, int H, int W, int vecs,
                                   uint4* __restrict__ out) {
+  pdl_enter();
   const long long total = (long long)NB * (2 * H) * (2 * W) * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -357,6 +370,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int NB, int H, in
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ x, int NB, int C, int H, int W, int Cpad,
                                     __half* __restrict__ out) {
+  pdl_enter();
   const long long total = (long long)NB * H * W * Cpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -375,6 +389,7 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ x, int NB, int C, int 
 __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int NB, int C, int H, int W,
                                     int Cpad, float mul, float add, float lo, float hi,
                                     __half* __restrict__ out) {
+  pdl_enter();
   const long long total = (long long)NB * C * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -393,6 +408,7 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int NB, int C,
 
 __global__ void im2col3x3_kernel(const __half* __restrict__ x, int NB, int H, int W, int C,
                                  int stride, int Ho, int Wo, int Kpad, __half* __restrict__ out) {
+  pdl_enter();
   const long long total = (long long)NB * Ho * Wo * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -415,6 +431,7 @@ __global__ void im2col3x3_kernel(const __half* __restrict__ x, int NB, int H, in
 
 __global__ void axpby_kernel(const __half* __restrict__ a, float sa, const __half* __restrict__ b,
                              float sb, long long n, __half* __restrict__ out) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float v = __half2float(a[i]) * sa;
@@ -425,6 +442,7 @@ __global__ void axpby_kernel(const __half* __restrict__ a, float sa, const __hal
 
 __global__ void add_rowvec_kernel(const uint4* __restrict__ a, const uint4* __restrict__ row,
                                   long long rows, int vecs, uint4* __restrict__ out) {
+  pdl_enter();
   const long long total = rows * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -442,6 +460,7 @@ __global__ void ddim_step_kernel(const __half* __restrict__ eps, const __half* _
                                  long long half_n, float guidance, const float* __restrict__ coef,
                                  const int* __restrict__ step, __half* __restrict__ x_prev,
                                  __half* __restrict__ pred_x0) {
+  pdl_enter();
   const int st = step ? *step : 0;
   // torch.full(..., dtype=fp16) rounds each coefficient to fp16 first (ddim.py:160-163)
   const float a_t = rh(coef[st * 4 + 0]);
@@ -470,6 +489,7 @@ __global__ void ddim_step_kernel(const __half* __restrict__ eps, const __half* _
 // out[(b*nWh + wy)*nWw + wx][iy*ws+ix][c] = xpad[b, (wy*ws+iy+shift)%Hp, (wx*ws+ix+shift)%Wp, c]
 __global__ void window_gather_kernel(const uint4* __restrict__ x, int B, int H, int W, int vecs,
                                      int ws, int shift, int Hp, int Wp, uint4* __restrict__ out) {
+  pdl_enter();
   const long long total = (long long)B * Hp * Wp * vecs;
   const int nWw = Wp / ws, nWh = Hp / ws;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -493,6 +513,7 @@ __global__ void window_gather_kernel(const uint4* __restrict__ x, int B, int H, 
 __global__ void window_scatter_kernel(const uint4* __restrict__ win, int B, int H, int W, int vecs,
                                       int ws, int shift, int Hp, int Wp,
                                       const uint4* __restrict__ residual, uint4* __restrict__ out) {
+  pdl_enter();
   const long long total = (long long)B * H * W * vecs;
   const int nWw = Wp / ws, nWh = Hp / ws;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -524,6 +545,7 @@ __global__ void window_scatter_kernel(const uint4* __restrict__ win, int B, int 
 // [(0,0),(1,0),(0,1),(1,1)] (dy,dx) along channels.
 __global__ void patch_merge_kernel(const uint4* __restrict__ x, int B, int H, int W, int vecs,
                                    uint4* __restrict__ out) {
+  pdl_enter();
   const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
   const long long total = (long long)B * H2 * W2 * 4 * vecs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -550,6 +572,7 @@ __global__ void patch_merge_kernel(const uint4* __restrict__ x, int B, int H, in
 template <typename T>
 __global__ void patchify_kernel(const T* __restrict__ x, int B, int C, int H, int W, int P, int Kpad,
                                 __half* __restrict__ out) {
+  pdl_enter();
   const int Hp = (H + P - 1) / P, Wp = (W + P - 1) / P;
   const long long total = (long long)B * Hp * Wp * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -604,10 +627,10 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   if (ppc < min_ppc) ppc = min_ppc;
   chunks = (HW + ppc - 1) / ppc;
   dim3 grid((unsigned)chunks, (unsigned)NB);
-  gn_stats_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2,
+  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), (size_t)(0), st, static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2,
                                             HW, groups, ppc, dws);
   if (int rc = check_launch("gn_stats")) return rc;
-  gn_apply_kernel<<<grid, threads, 0, st>>>(static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, HW,
+  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), (size_t)(0), st, static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, HW,
                                             groups, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
                                             eps, silu, dws, static_cast<__half*>(out), ppc,
                                             1.0 / ((double)HW * (C / groups)));
@@ -627,11 +650,11 @@ extern "C" PFD_API int pfd_layernorm_f16(const void* x, const void* res, int64_t
   const __half* gp = static_cast<const __half*>(gamma);
   const __half* bp = static_cast<const __half*>(beta);
   __half* op = static_cast<__half*>(out);
-  if (vecs <= 32) layernorm_kernel<1><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
-  else if (vecs <= 64) layernorm_kernel<2><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
-  else if (vecs <= 128) layernorm_kernel<4><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
-  else if (vecs <= 256) layernorm_kernel<8><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
-  else layernorm_kernel<16><<<grid, 256, 0, st>>>(xp, rp, rows, C, gp, bp, eps, op);
+  if (vecs <= 32) launch_k(layernorm_kernel<1>, dim3(grid), dim3(256), (size_t)(0), st, xp, rp, rows, C, gp, bp, eps, op);
+  else if (vecs <= 64) launch_k(layernorm_kernel<2>, dim3(grid), dim3(256), (size_t)(0), st, xp, rp, rows, C, gp, bp, eps, op);
+  else if (vecs <= 128) launch_k(layernorm_kernel<4>, dim3(grid), dim3(256), (size_t)(0), st, xp, rp, rows, C, gp, bp, eps, op);
+  else if (vecs <= 256) launch_k(layernorm_kernel<8>, dim3(grid), dim3(256), (size_t)(0), st, xp, rp, rows, C, gp, bp, eps, op);
+  else launch_k(layernorm_kernel<16>, dim3(grid), dim3(256), (size_t)(0), st, xp, rp, rows, C, gp, bp, eps, op);
   return check_launch("layernorm");
 }
 
@@ -649,7 +672,7 @@ extern "C" PFD_API int pfd_softmax_f16(void* s, int64_t batch, int32_t rows, int
     cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 4);
     attr = true;
   }
-  softmax_rows_kernel<<<(unsigned)nrows, threads, cols * sizeof(float), st>>>(
+  launch_k(softmax_rows_kernel, dim3((unsigned)nrows), dim3(threads), (size_t)(cols * sizeof(float)), st, 
       static_cast<__half*>(s), batch, rows, cols, ld, scale, static_cast<const __half*>(bias), nheads,
       static_cast<const __half*>(mask), nwin);
   return check_launch("softmax");
@@ -658,7 +681,7 @@ extern "C" PFD_API int pfd_softmax_f16(void* s, int64_t batch, int32_t rows, int
 extern "C" PFD_API int pfd_timestep_embedding_f16(const int64_t* t, int32_t n, int32_t dim, float max_period,
                                           void* out, void* stream) {
   const int total = n * (dim / 2);
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), (size_t)(0), static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(t), n, dim, max_period, static_cast<__half*>(out));
   return check_launch("timestep_embedding");
 }
@@ -667,7 +690,7 @@ extern "C" PFD_API int pfd_upsample2x_f16(const void* x, int32_t NB, int32_t H, 
                                   void* stream) {
   if (C % 8) return set_error("pfd_upsample2x_f16: C=%d", C);
   const long long total = (long long)NB * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(x), NB, H, W, C / 8, static_cast<uint4*>(out));
   return check_launch("upsample2x");
 }
@@ -677,16 +700,16 @@ extern "C" PFD_API int pfd_nchw_to_nhwc_f16(const void* x, int32_t src_is_f32, i
   const long long total = (long long)NB * H * W * Cpad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src_is_f32)
-    nchw_to_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(x), NB, C, H, W, Cpad, static_cast<__half*>(out));
+    launch_k(nchw_to_nhwc_kernel<float>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, static_cast<const float*>(x), NB, C, H, W, Cpad, static_cast<__half*>(out));
   else
-    nchw_to_nhwc_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(x), NB, C, H, W, Cpad, static_cast<__half*>(out));
+    launch_k(nchw_to_nhwc_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, static_cast<const __half*>(x), NB, C, H, W, Cpad, static_cast<__half*>(out));
   return check_launch("nchw_to_nhwc");
 }
 
 extern "C" PFD_API int pfd_nhwc_to_nchw_f16(const void* x, int32_t NB, int32_t C, int32_t H, int32_t W, int32_t Cpad,
                                     float mul, float add, float lo, float hi, void* out, void* stream) {
   const long long total = (long long)NB * C * H * W;
-  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(nhwc_to_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(x), NB, C, H, W, Cpad, mul, add, lo, hi, static_cast<__half*>(out));
   return check_launch("nhwc_to_nchw");
 }
@@ -696,14 +719,14 @@ extern "C" PFD_API int pfd_im2col3x3_f16(const void* x, int32_t NB, int32_t H, i
   if (Kpad < 9 * C || Kpad % 8) return set_error("pfd_im2col3x3_f16: Kpad=%d for C=%d", Kpad, C);
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   const long long total = (long long)NB * Ho * Wo * Kpad;
-  im2col3x3_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(im2col3x3_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(x), NB, H, W, C, stride, Ho, Wo, Kpad, static_cast<__half*>(out));
   return check_launch("im2col3x3");
 }
 
 extern "C" PFD_API int pfd_axpby_f16(const void* a, float sa, const void* b, float sb, int64_t n, void* out,
                              void* stream) {
-  axpby_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(axpby_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(a), sa, static_cast<const __half*>(b), sb, n, static_cast<__half*>(out));
   return check_launch("axpby");
 }
@@ -711,7 +734,7 @@ extern "C" PFD_API int pfd_axpby_f16(const void* a, float sa, const void* b, flo
 extern "C" PFD_API int pfd_add_rowvec_f16(const void* a, const void* row, int64_t rows, int32_t C, void* out,
                                   void* stream) {
   if (C % 8) return set_error("pfd_add_rowvec_f16: C=%d", C);
-  add_rowvec_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(add_rowvec_kernel, dim3(grid_for(rows * (C / 8), 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(a), static_cast<const uint4*>(row), rows, C / 8, static_cast<uint4*>(out));
   return check_launch("add_rowvec");
 }
@@ -719,7 +742,7 @@ extern "C" PFD_API int pfd_add_rowvec_f16(const void* a, const void* row, int64_
 extern "C" PFD_API int pfd_ddim_step_f16(const void* eps, const void* x, int64_t half_n, float guidance,
                                  const float* coef, const int32_t* step, void* x_prev, void* pred_x0,
                                  void* stream) {
-  ddim_step_kernel<<<grid_for(half_n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(ddim_step_kernel, dim3(grid_for(half_n, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(eps), static_cast<const __half*>(x), half_n, guidance, coef, step,
       static_cast<__half*>(x_prev), static_cast<__half*>(pred_x0));
   return check_launch("ddim_step");
@@ -730,7 +753,7 @@ extern "C" PFD_API int pfd_window_gather_f16(const void* x, int32_t B, int32_t H
   if (C % 8) return set_error("pfd_window_gather_f16: C=%d", C);
   const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
   const long long total = (long long)B * Hp * Wp * (C / 8);
-  window_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(window_gather_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(x), B, H, W, C / 8, ws, shift, Hp, Wp, static_cast<uint4*>(out));
   return check_launch("window_gather");
 }
@@ -741,7 +764,7 @@ extern "C" PFD_API int pfd_window_scatter_f16(const void* win, int32_t B, int32_
   if (C % 8) return set_error("pfd_window_scatter_f16: C=%d", C);
   const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
   const long long total = (long long)B * H * W * (C / 8);
-  window_scatter_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(window_scatter_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(win), B, H, W, C / 8, ws, shift, Hp, Wp,
       static_cast<const uint4*>(residual), static_cast<uint4*>(out));
   return check_launch("window_scatter");
@@ -751,7 +774,7 @@ extern "C" PFD_API int pfd_patch_merge_gather_f16(const void* x, int32_t B, int3
                                           void* out, void* stream) {
   if (C % 8) return set_error("pfd_patch_merge_gather_f16: C=%d", C);
   const long long total = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * 4 * (C / 8);
-  patch_merge_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(patch_merge_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(x), B, H, W, C / 8, static_cast<uint4*>(out));
   return check_launch("patch_merge");
 }
@@ -762,8 +785,8 @@ extern "C" PFD_API int pfd_patchify_f16(const void* x, int32_t src_is_f32, int32
   const long long total = (long long)B * ((H + P - 1) / P) * ((W + P - 1) / P) * Kpad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src_is_f32)
-    patchify_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(x), B, C, H, W, P, Kpad, static_cast<__half*>(out));
+    launch_k(patchify_kernel<float>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, static_cast<const float*>(x), B, C, H, W, P, Kpad, static_cast<__half*>(out));
   else
-    patchify_kernel<__half><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __half*>(x), B, C, H, W, P, Kpad, static_cast<__half*>(out));
+    launch_k(patchify_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, static_cast<const __half*>(x), B, C, H, W, P, Kpad, static_cast<__half*>(out));
   return check_launch("patchify");
 }

@@ -159,6 +159,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_g;
+  // prologue above overlapped the previous kernel's tail; global data may only be touched from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_nb;
   const int total_tiles = m_tiles * p.n_tiles;
@@ -428,6 +431,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 // (bias, per-image row add, activation, residual) with the same generic output addressing.
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const __grid_constant__ GemmParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_nb;
   const long long rows_pad = (long long)m_tiles * BM;
   const int vecs = p.N / 8;
@@ -569,7 +574,7 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_done = true;
   }
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
+  launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
   return check_launch("pfd_gemm_f16");
 }
 
@@ -735,6 +740,6 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   const long long vec_items = m_tiles * BM * (long long)(d->N / 8);
   long long fgrid = (vec_items + 255) / 256;
   if (fgrid > 8LL * sms) fgrid = 8LL * sms;
-  splitk_finish_kernel<<<(unsigned)fgrid, 256, 0, st>>>(p);
+  launch_k(splitk_finish_kernel, dim3((unsigned)fgrid), dim3(256), 0, st, p);
   return check_launch("pfd_gemm_f16(split-K finish)");
 }
