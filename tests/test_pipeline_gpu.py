@@ -181,7 +181,7 @@ def test_seecoder_512_and_sampler_graph_reuse(env):
 
     def run(seed):
         torch.manual_seed(seed)
-        x, _ = sampler.sample(steps=3, x_info={"type": "image"},
+        x, _ = sampler.sample(steps=4, x_info={"type": "image"},
                               c_info={"type": "image", "conditioning": c.repeat(2, 1, 1),
                                       "unconditional_conditioning": torch.zeros_like(c.repeat(2, 1, 1)),
                                       "unconditional_guidance_scale": 2.0, "control": None},
@@ -190,6 +190,32 @@ def test_seecoder_512_and_sampler_graph_reuse(env):
     a, b, a2 = run(1), run(2), run(1)
     assert torch.isfinite(a.float()).all() and (a.float() - b.float()).abs().max().item() > 0.1
     assert (a.float() - a2.float()).abs().max().item() < 5e-2
+
+
+def test_sampler_without_cfg_and_with_eta(env):
+    """guidance == 1.0 skips the CFG batch (ddim.py:142-144) -> compare with the oracle sampler; eta > 0 adds
+    sigma_t * noise every step (ddim.py:168) -> must stay finite and differ from the eta = 0 result."""
+    net, gold, inp = env
+    from oracle import pfd_oracle as O
+    from pfd_b200 import DDIMSampler
+    cond = inp["cond"].half()
+    sampler = DDIMSampler(net)
+    x, _ = sampler.sample(steps=4, x_info={"type": "image", "xt": inp["x_T"].half()},
+                          c_info={"type": "image", "conditioning": cond, "unconditional_conditioning": None,
+                                  "unconditional_guidance_scale": 1.0, "control": None},
+                          shape=[1, 4, 16, 16], verbose=False, eta=0.0)
+    sd = {k[len("diffuser.image."):]: v.detach().float().cpu() for k, v in net.state_dict().items()
+          if k.startswith("diffuser.image.")}
+    with torch.no_grad():
+        ref = O.ddim_sample(sd, O.UNET_SD15, O.schedule_buffers()["alphas_cumprod"], steps=4, x_T=inp["x_T"].cpu(),
+                            cond=inp["cond"].cpu().half().float(), uncond=None, guidance=1.0)
+    _check("ddim 4-step latent, no CFG", x, ref, mse_tol=1e-3, rel_tol=2e-2)
+    torch.manual_seed(3)
+    xe, _ = sampler.sample(steps=4, x_info={"type": "image", "xt": inp["x_T"].half()},
+                           c_info={"type": "image", "conditioning": cond, "unconditional_conditioning": None,
+                                   "unconditional_guidance_scale": 1.0, "control": None},
+                           shape=[1, 4, 16, 16], verbose=False, eta=0.5)
+    assert torch.isfinite(xe.float()).all() and (xe.float() - x.float()).abs().max().item() > 1e-2
 
 
 def test_native_library_is_what_ran():
