@@ -193,6 +193,16 @@ PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const void* vt, voi
                                int32_t k_rows, float scale, int64_t vt_pitch, int64_t o_sb, int64_t o_sq,
                                int32_t reserved, void* stream);
 
+/*
+ * Flash attention v2: q / k / v are 4-D strided views [B, heads, N, d] (strides {batch, head, row} in elements,
+ * d contiguous), so one projection GEMM can emit q|k|v (or k|v) side by side; V is read in its natural
+ * [keys, d] layout (MN-major tcgen05 operand).  Same semantics / output layout as pfd_flash_attn_f16.
+ */
+PFD_API int pfd_flash_attn_qkv_f16(const void* q, const void* k, const void* v, void* out, int32_t B,
+                                   int32_t heads, int32_t Nq, int32_t Nk, int32_t d, const int64_t* q_strides,
+                                   const int64_t* k_strides, const int64_t* v_strides, float scale,
+                                   int64_t o_sb, int64_t o_sq, void* stream);
+
 /* PatchEmbed gather (swin.py:479-489): NCHW image (fp16/fp32) -> [B, ceil(H/P), ceil(W/P), Kpad] rows in
  * the K order of the flattened conv weight [O, C*P*P]; zero padding for ragged H/W and K..Kpad. */
 PFD_API int pfd_patchify_f16(const void* x, int32_t src_is_f32, int32_t B, int32_t C, int32_t H,

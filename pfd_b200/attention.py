@@ -22,6 +22,8 @@ from . import native as nv
 # fused tcgen05 flash attention for bias-free attention; False falls back to the materialised
 # QK^T GEMM -> softmax -> PV GEMM pipeline (still all pfd_b200 kernels) — used by tests to cross-check.
 USE_FLASH = True
+# v2: fused q|k|v projection GEMM + strided / MN-major-V flash kernel (pfd_flash_attn_qkv_f16)
+USE_FLASH_V2 = True
 
 
 def ceil8(n: int) -> int:
@@ -79,3 +81,26 @@ def attend(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, B: int, heads:
 def _view_cols(s: torch.Tensor, cols: int) -> torch.Tensor:
     # as_strided view keeps the row pitch (stride(1)) while exposing only the valid columns
     return s.as_strided((s.shape[0], s.shape[1], cols), (s.stride(0), s.stride(1), 1))
+
+
+def project_heads_fused(x2d: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], B: int, N: int,
+                        heads: int, d: int, nsec: int) -> torch.Tensor:
+    """ONE projection GEMM for `nsec` stacked projections (q|k|v or k|v): x2d [B*N, Cin] @ w[nsec*heads*d, Cin]^T
+    -> [B, nsec*heads, Np, d] (virtual heads).  Section s of the result is out[:, s*heads:(s+1)*heads]."""
+    Np = ceil8(N)
+    vh = nsec * heads
+    alloc = torch.zeros if Np != N else torch.empty
+    out = alloc((B, vh, Np, d), device=x2d.device, dtype=torch.float16)
+    ld = x2d.stride(0)
+    nv.gemm_raw([(x2d, 1, x2d.shape[1], (ld, ld * N, ld * N))], in_w=N, in_h=1, stride=1, W=N, H=1, NB=B, w=w,
+                N=w.shape[0], K=w.stride(0), bias=b, out=out, so=(vh * Np * d, 0, 0, d, Np * d, 1), ndiv=1, cdiv=d)
+    return out
+
+
+def attend_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, Nq: int, Nk: int, scale: float,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Flash attention v2 on strided [B, heads, Np, d] views -> [B, Nq, heads*d]."""
+    B, heads, _, d = q.shape
+    if out is None:
+        out = torch.empty((B, Nq, heads * d), device=q.device, dtype=torch.float16)
+    return nv.flash_attn_qkv(q, k, v, Nq=Nq, Nk=Nk, scale=scale, out=out)

@@ -1,0 +1,411 @@
+// Flash attention v2 for sm_100a: same pipeline as attention.cu, but q / k / v are arbitrary 4-D strided
+// views [B, heads, N, d] (so ONE projection GEMM can emit q|k|v, or k|v, side by side), V is consumed
+// in its natural [keys, d] layout as an MN-major B operand of the PV MMA (no V^T scatter in the
+// projection epilogue), and the softmax row sums come from a second tiny MMA  L += P x ones[64 x 16].
+// Fused flash attention for sm_100a (tcgen05 + TMEM + TMA), used for the UNet / ControlNet
+// self- and cross-attention (attention.py:178-201):  O = softmax(Q K^T * scale) V  per (batch, head)
+// without ever materialising the [N, Nk] score matrix in HBM.
+//
+//   CTA = 128 query rows of one (batch, head); KV processed in blocks of 64 keys.
+//   warp 0      : TMA producer (Q once; K / V^T blocks through a 2-stage ring)
+//   warp 1      : tcgen05.mma issuer   S_j = Q K_j^T  (TMEM, double buffered)   O += P_j V_j (TMEM)
+//   warps 2..5  : softmax: thread r owns query row r (TMEM lane r) -> no cross-thread reductions;
+//                 two passes over S_j in TMEM (max, then exp/sum), P_j written to shared memory in
+//                 the K-major 128B-swizzled layout the PV MMA reads, O rescaled in TMEM when the
+//                 running max moves, final O / l written as [B, Nq, heads*d].
+//   Logits are rounded to fp16 like the reference's fp16 score tensor (fp16(q.k * scale)); the softmax
+//   runs on packed half2 (HMNMX2 / HSUB2 / HMUL2 / MUFU.EX2.F16x2, two keys per instruction) and the row
+//   sum l comes for free from the tensor core: row d of the V^T tile is all ones, so column d of the
+//   O accumulator is sum_j p_j (rescaled together with O).
+//   Shared memory is kept small (60-152 KB) so two CTAs share an SM for d <= 80 and overlap each
+//   other's softmax (MUFU/ALU) and MMA phases.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/pfd_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pfd {
+
+constexpr int FA_BQ = 128;
+constexpr int FA_BKV = 64;
+constexpr int FA_THREADS = 192;
+
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct alignas(64) Flash2Params {
+  CUtensorMap tmQ, tmK, tmV;
+  int Nq, Nk, heads, d;
+  int nblk;
+  float scale;
+  __half* out;
+  long long o_sb, o_sq, o_sh;  // element strides: batch, query row, head
+};
+
+template <int DCH>
+struct Flash2Cfg {
+  static constexpr int Q_BYTES = DCH * FA_BQ * 128;
+  static constexpr int K_BYTES = DCH * FA_BKV * 128;
+  static constexpr int DN = DCH == 1 ? 80 : (DCH == 2 ? 144 : 208);  // max rows of the V^T tile (d + ones row, padded)
+  static constexpr int P_BYTES = FA_BQ * 128;
+  static constexpr int NPB = 1;                  // P buffers
+  // S accumulators in TMEM: one for d <= 64 (64 + 48 columns -> 128-column allocation, ~60 KB smem ->
+  // three CTAs per SM overlap each other's TMEM-load / MUFU / smem / MMA phases), two otherwise
+  static constexpr int NSB = DCH == 1 ? 1 : 2;
+  static constexpr int ONES_BYTES = 16 * 128;      // K-major [16 x 64] tile of ones: B operand of the row-sum MMA
+  static int smem_bytes(int) { return Q_BYTES + 2 * (2 * K_BYTES) + NPB * P_BYTES + ONES_BYTES + 1024 + 128; }
+};
+
+template <int DCH>
+__global__ void __launch_bounds__(FA_THREADS)
+flash_attn2_kernel(const __grid_constant__ Flash2Params p) {
+  using Cfg = Flash2Cfg<DCH>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const int d = p.d;
+  const int dN = (d + 15) & ~15;       // PV MMA N (head dim padded to 16)
+  const int V_BYTES = Cfg::K_BYTES;    // V stage: [64 keys x DCH*64] like K
+  const uint32_t need_cols = Cfg::NSB * FA_BKV + dN + 16;   // S buffer(s) | O | L (row sums)
+  const uint32_t tmem_cols = need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u);
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + Cfg::Q_BYTES;                  // [2][K_BYTES]
+  const uint32_t sV = sK + 2 * Cfg::K_BYTES;              // [2][V_BYTES]
+  const uint32_t sP = sV + 2 * V_BYTES;
+  const uint32_t sOnes = sP + Cfg::NPB * Cfg::P_BYTES;
+  const uint32_t bars = sOnes + Cfg::ONES_BYTES;
+  uint8_t* gP = gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES;
+  const uint32_t bar_q = bars;
+  auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto bar_kv_empty = [&](int s) { return bars + 8u * (3 + s); };
+  auto bar_s_full = [&](int s) { return bars + 8u * (5 + s); };
+  auto bar_s_free = [&](int s) { return bars + 8u * (7 + s); };
+  const uint32_t bar_p_ready = bars + 8u * 9;
+  const uint32_t bar_pv_done = bars + 8u * 10;
+  const uint32_t tmem_slot = bars + 8u * 11;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(
+      gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES + Cfg::NPB * Cfg::P_BYTES + Cfg::ONES_BYTES + 8 * 11);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FA_BQ;
+  const int bh = blockIdx.y;
+  const int hb = bh % p.heads, bb = bh / p.heads;
+  const int nblk = p.nblk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_kv_full(s), 1);
+      mbar_init(bar_kv_empty(s), 1);
+      mbar_init(bar_s_full(s), 1);
+      mbar_init(bar_s_free(s), 128);
+    }
+    mbar_init(bar_p_ready, 128);
+    mbar_init(bar_pv_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_rt(tmem_slot, tmem_cols);
+  if (warp >= 2) {
+    uint8_t* gOnes = gP + Cfg::NPB * Cfg::P_BYTES;
+    const int t = threadIdx.x - 64;                   // 128 threads x 16 B = 2 KB of fp16 ones
+    *reinterpret_cast<uint4*>(gOnes + t * 16) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  const uint32_t tmem_O = tmem_base + Cfg::NSB * FA_BKV;
+  const uint32_t tmem_L = tmem_O + dN;
+  pdl_wait();                  // q / k / v are produced by the preceding projection GEMMs
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, Cfg::Q_BYTES);
+      for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * FA_BQ * 128, &p.tmQ, bar_q, c * 64, q0, hb, bb);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1, u = j >> 1;
+        if (u >= 1) mbar_wait(bar_kv_empty(st), (u - 1) & 1);
+        mbar_expect_tx(bar_kv_full(st), 2 * Cfg::K_BYTES);
+        for (int c = 0; c < DCH; ++c)
+          tma_load_4d(sK + st * Cfg::K_BYTES + c * FA_BKV * 128, &p.tmK, bar_kv_full(st), c * 64, j * FA_BKV, hb, bb);
+        for (int c = 0; c < DCH; ++c)
+          tma_load_4d(sV + st * V_BYTES + c * FA_BKV * 128, &p.tmV, bar_kv_full(st), c * 64, j * FA_BKV, hb, bb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(FA_BKV);
+      const uint32_t idesc_o = make_idesc_f16((uint32_t)dN) | (1u << 16);   // B (= V tile [keys, d]) is MN-major
+      const uint32_t idesc_l = make_idesc_f16(16);
+      auto issue_S = [&](int j) {
+        const int st = j & 1;
+        const int sb = j % Cfg::NSB;
+        const uint32_t tS = tmem_base + sb * FA_BKV;
+        bool first = true;
+        for (int c = 0; c < DCH; ++c) {
+          const int rem = d - c * 64;
+          if (rem <= 0) break;
+          const int ksteps = rem >= 64 ? 4 : (rem + 15) / 16;
+          const uint64_t ad = make_sw128_kmajor_desc(sQ + c * FA_BQ * 128);
+          const uint64_t bd = make_sw128_kmajor_desc(sK + st * Cfg::K_BYTES + c * FA_BKV * 128);
+          for (int s = 0; s < ksteps; ++s) {
+            umma_f16(tS, ad + 2u * s, bd + 2u * s, idesc_s, first ? 0u : 1u);
+            first = false;
+          }
+        }
+        umma_commit(bar_s_full(sb));
+      };
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv_full(0), 0);
+      tc_fence_after();
+      issue_S(0);
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {
+          const int st = (j + 1) & 1, u = (j + 1) >> 1;
+          const int sb = (j + 1) % Cfg::NSB, us = (j + 1) / Cfg::NSB;
+          mbar_wait(bar_kv_full(st), u & 1);
+          if (us >= 1) mbar_wait(bar_s_free(sb), (us - 1) & 1);
+          tc_fence_after();
+          issue_S(j + 1);
+        }
+        mbar_wait(bar_p_ready, j & 1);
+        tc_fence_after();
+        const int st = j & 1;
+        const uint64_t ad = make_sw128_kmajor_desc(sP + (Cfg::NPB == 2 ? (j & 1) * Cfg::P_BYTES : 0));
+        const uint64_t od = make_sw128_kmajor_desc(sOnes);
+#pragma unroll
+        for (int s = 0; s < FA_BKV / 16; ++s) {
+          // 16 keys = 16 rows x 128 B of the V tile; 64-column chunks of d are FA_BKV*128 B apart (LBO)
+          const uint64_t bd = make_sw128_mnmajor_desc(sV + st * V_BYTES + s * 16 * 128, FA_BKV * 128);
+          umma_f16(tmem_O, ad + 2u * s, bd, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
+          umma_f16(tmem_L, ad + 2u * s, od + 2u * s, idesc_l, (j > 0 || s > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_kv_empty(st));
+        umma_commit(bar_pv_done);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / output warps
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    const float sc = p.scale;
+    const __half2 log2e2 = __float2half2_rn(LOG2E);
+    const __half2 ninf2 = __float2half2_rn(-INFINITY);
+    float m = -INFINITY;
+    uint8_t* prow0 = gP + row * 128;
+    const int rsw = row & 7;
+    for (int j = 0; j < nblk; ++j) {
+      const int sb = j % Cfg::NSB, us = j / Cfg::NSB;
+      const int kvalid = min(FA_BKV, p.Nk - j * FA_BKV);
+      const bool partial = kvalid < FA_BKV;            // block-uniform
+      mbar_wait(bar_s_full(sb), us & 1);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + lane_off + sb * FA_BKV;
+      // single pass over S (TMEM reads are the scarce resource: 64 B/clk/SM): logits -> packed fp16 in
+      // registers (32 x half2 for 64 keys), running max with HMNMX2
+      __half2 v[FA_BKV / 2];
+      __half2 mx2 = ninf2;
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tS, r0);
+        tmem_ld32(tS + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          v[i >> 1] = __floats2half2_rn(__uint_as_float(r0[i]) * sc, __uint_as_float(r0[i + 1]) * sc);
+          v[16 + (i >> 1)] = __floats2half2_rn(__uint_as_float(r1[i]) * sc, __uint_as_float(r1[i + 1]) * sc);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_s_free(sb));                      // S buffer may now be overwritten by the next QK^T
+      if (partial) {
+#pragma unroll
+        for (int i = 0; i < FA_BKV / 2; ++i) {
+          if (2 * i >= kvalid) v[i] = ninf2;
+          else if (2 * i + 1 >= kvalid) v[i] = __halves2half2(__low2half(v[i]), __float2half_rn(-INFINITY));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < FA_BKV / 2; ++i) mx2 = __hmax2(mx2, v[i]);
+      const float m_new = fmaxf(m, fmaxf(__low2float(mx2), __high2float(mx2)));
+      const float alpha = (j == 0) ? 0.f : fast_exp2((m - m_new) * LOG2E);
+      const __half2 mh2 = __float2half2_rn(m_new);     // exact: m_new is an fp16 value
+      if (Cfg::NPB == 1 && j > 0) {
+        mbar_wait(bar_pv_done, (j - 1) & 1);           // single P buffer: PV_{j-1} must have consumed it
+        tc_fence_after();
+      }
+      uint8_t* prow = prow0 + (Cfg::NPB == 2 ? (j & 1) * Cfg::P_BYTES : 0);
+      // p = 2^((v - m) * log2e) on packed halves -> P tile in shared memory (swizzled K-major A operand)
+#pragma unroll
+      for (int g = 0; g < FA_BKV / 8; ++g) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __half2 t = __hmul2(__hsub2(v[g * 4 + i], mh2), log2e2);
+          pk[i] = ex2_f16x2(*reinterpret_cast<const uint32_t*>(&t));
+        }
+        *reinterpret_cast<uint4*>(prow + ((g ^ rsw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      m = m_new;
+      if (Cfg::NPB == 2 && j > 0) {
+        // double-buffered P: exp/write of this block overlapped PV_{j-1}; O must be stable before the
+        // rescale below and before PV_j accumulates into it (also frees P[(j+1)&1] for the next block)
+        mbar_wait(bar_pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      // rescale the running output (and its row-sum column) when this warp's maxima moved
+      if (j > 0) {
+        const bool need = __any_sync(0xffffffffu, alpha != 1.f);
+        if (need) {
+          for (int c = 0; c < dN / 16 + 1; ++c) {   // O columns, then the 16 row-sum columns
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_off + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_off + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p_ready);
+    }
+    // ---- epilogue: O / l -> [B, Nq, heads*d]   (l = first row-sum column)
+    mbar_wait(bar_pv_done, (nblk - 1) & 1);
+    tc_fence_after();
+    const uint32_t lraw = tmem_ld1(tmem_L + lane_off);
+    tmem_ld_wait();
+    const float l = __uint_as_float(lraw);
+    const int q = q0 + row;
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const int b = bh / p.heads, h = bh % p.heads;
+    __half* orow = p.out + (long long)b * p.o_sb + (long long)q * p.o_sq + (long long)h * p.o_sh;
+    for (int c = 0; c < (d + 15) / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_off + c * 16, o);
+      tmem_ld_wait();
+      if (q < p.Nq) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int col = c * 16 + h8 * 8;
+          if (col < d) {
+            uint4 v;
+            __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              hv[i] = __floats2half2_rn(__uint_as_float(o[h8 * 8 + 2 * i]) * inv,
+                                        __uint_as_float(o[h8 * 8 + 2 * i + 1]) * inv);
+            *reinterpret_cast<uint4*>(orow + col) = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_rt(tmem_base, tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode4d_fa(CUtensorMap* m, const void* ptr, int d, int rows, int heads, int B, long long sr,
+                       long long sh, long long sb, int box_rows, const char* what) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return set_error("cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(fp);
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sr * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error("flash attention v2 tensor map (%s) encode failed: CUresult %d d=%d rows=%d heads=%d B=%d strides[%lld,%lld,%lld]",
+                     what, (int)r, d, rows, heads, B, sr, sh, sb);
+  return 0;
+}
+
+template <int DCH>
+static int launch_flash2(const Flash2Params& p, dim3 grid, cudaStream_t st) {
+  using Cfg = Flash2Cfg<DCH>;
+  static bool done = false;
+  const int smem = Cfg::smem_bytes(0);
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn2_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(flash2 DCH=%d): %s", DCH, cudaGetErrorString(e));
+    done = true;
+  }
+  launch_k(flash_attn2_kernel<DCH>, grid, dim3(FA_THREADS), (size_t)smem, st, p);
+  return check_launch("pfd_flash_attn_qkv_f16");
+}
+
+}  // namespace pfd
+
+using namespace pfd;
+
+extern "C" PFD_API int pfd_flash_attn_qkv_f16(const void* q, const void* k, const void* v, void* out, int32_t B,
+                                              int32_t heads, int32_t Nq, int32_t Nk, int32_t d,
+                                              const int64_t* q_strides, const int64_t* k_strides,
+                                              const int64_t* v_strides, float scale, int64_t o_sb, int64_t o_sq,
+                                              void* stream) {
+  if (d % 8 || d <= 0 || d > 192) return set_error("pfd_flash_attn_qkv_f16: head dim %d unsupported", d);
+  if (Nq <= 0 || Nk <= 0) return set_error("pfd_flash_attn_qkv_f16: empty problem");
+  for (int i = 0; i < 3; ++i)
+    if (q_strides[i] % 8 || k_strides[i] % 8 || v_strides[i] % 8)
+      return set_error("pfd_flash_attn_qkv_f16: strides must be multiples of 8 elements");
+  Flash2Params p;
+  memset(&p, 0, sizeof(p));
+  // strides: {batch, head, row} in elements; rows are contiguous over d
+  if (int rc = encode4d_fa(&p.tmQ, q, d, Nq, heads, B, q_strides[2], q_strides[1], q_strides[0], FA_BQ, "Q")) return rc;
+  if (int rc = encode4d_fa(&p.tmK, k, d, Nk, heads, B, k_strides[2], k_strides[1], k_strides[0], FA_BKV, "K")) return rc;
+  if (int rc = encode4d_fa(&p.tmV, v, d, Nk, heads, B, v_strides[2], v_strides[1], v_strides[0], FA_BKV, "V")) return rc;
+  p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.d = d;
+  p.nblk = (Nk + FA_BKV - 1) / FA_BKV;
+  p.scale = scale;
+  p.out = static_cast<__half*>(out);
+  p.o_sb = o_sb; p.o_sq = o_sq; p.o_sh = d;
+  dim3 grid((Nq + FA_BQ - 1) / FA_BQ, (unsigned)(B * heads));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d <= 64) return launch_flash2<1>(p, grid, st);
+  if (d <= 128) return launch_flash2<2>(p, grid, st);
+  return launch_flash2<3>(p, grid, st);
+}

@@ -121,6 +121,18 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major, 128-byte-swizzled operand tile: rows = K index (128 B each = 64 contiguous MN elements), 8-row
+// groups 1024 B apart (SBO); further 64-element MN blocks `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16, A/B fp16 K-major, fp32 accumulate, M=128, N=n.
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t n) {
   return (1u << 4)               // c_format = F32

@@ -20,7 +20,8 @@ import torch
 import torch.nn as nn
 
 from . import native as nv
-from .attention import attend, ceil8, project_heads
+from . import attention as att
+from .attention import attend, attend_qkv, ceil8, project_heads, project_heads_fused
 from .modules import (Conv2d, GroupNorm, IndexedSequential, LayerNorm, Linear, cached, pk_conv3,
                       pk_conv3_small, pk_lin, pk_mat, pk_norm)
 
@@ -149,11 +150,21 @@ def run_resblock(rb: ResBlock, x: torch.Tensor, x2: Optional[torch.Tensor], emb_
     return nv.conv3x3(h, w2, b2, skip=[x] if x2 is None else [x, x2])
 
 
+def _cat_weights(owner: nn.Module, key: str, lins) -> torch.Tensor:
+    """Row-concatenated fp16 weights of bias-free Linear layers (fused q|k|v / k|v projection)."""
+    return cached(owner, key, [l.weight for l in lins],
+                  lambda: torch.cat([l.weight.detach().half() for l in lins], 0).contiguous())
+
+
 def context_kv(st: SpatialTransformer, context: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """to_k / to_v of the cross-attention for a context [Bc, Nk, Cctx]; constant across DDIM steps."""
     blk = st.transformer_blocks[0]
     Bc, Nk, Cc = context.shape
     ctx2d = context.reshape(Bc * Nk, Cc)
+    if att.USE_FLASH_V2:
+        wkv = _cat_weights(blk.attn2, "kv_cat", [blk.attn2.to_k, blk.attn2.to_v])
+        kv = project_heads_fused(ctx2d, wkv, None, Bc, Nk, st.n_heads, st.d_head, 2)
+        return kv[:, :st.n_heads], kv[:, st.n_heads:]
     wk, _ = pk_lin(blk.attn2.to_k)
     wv, _ = pk_lin(blk.attn2.to_v)
     k = project_heads(ctx2d, wk, None, Bc, Nk, st.n_heads, st.d_head)
@@ -176,20 +187,28 @@ def run_spatial_transformer(st: SpatialTransformer, x: torch.Tensor, context: to
     g, b = pk_norm(blk.norm1)
     n1 = nv.layernorm(t, g, b, blk.norm1.eps)
     a = blk.attn1
-    q = project_heads(n1, pk_lin(a.to_q)[0], None, B, N, heads, d)
-    k = project_heads(n1, pk_lin(a.to_k)[0], None, B, N, heads, d)
-    vt = project_heads(n1, pk_lin(a.to_v)[0], None, B, N, heads, d, transposed=True)
-    o = attend(q, k, vt, B=B, heads=heads, Nq=N, Nk=N, scale=a.scale)
+    if att.USE_FLASH_V2:
+        qkv = project_heads_fused(n1, _cat_weights(a, "qkv_cat", [a.to_q, a.to_k, a.to_v]), None, B, N, heads, d, 3)
+        o = attend_qkv(qkv[:, :heads], qkv[:, heads:2 * heads], qkv[:, 2 * heads:], Nq=N, Nk=N, scale=a.scale)
+    else:
+        q = project_heads(n1, pk_lin(a.to_q)[0], None, B, N, heads, d)
+        k = project_heads(n1, pk_lin(a.to_k)[0], None, B, N, heads, d)
+        vt = project_heads(n1, pk_lin(a.to_v)[0], None, B, N, heads, d, transposed=True)
+        o = attend(q, k, vt, B=B, heads=heads, Nq=N, Nk=N, scale=a.scale)
     w, bb = pk_lin(a.to_out[0])
     t = nv.linear(o.reshape(B * N, inner), w, bb, residual=t)
     # --- cross attention (attention.py:304)
     g, b = pk_norm(blk.norm2)
     n2 = nv.layernorm(t, g, b, blk.norm2.eps)
     a = blk.attn2
-    q = project_heads(n2, pk_lin(a.to_q)[0], None, B, N, heads, d)
     if kv is None:
         kv = context_kv(st, context)
-    o = attend(q, kv[0], kv[1], B=B, heads=heads, Nq=N, Nk=context.shape[1], scale=a.scale)
+    if att.USE_FLASH_V2:
+        q = project_heads_fused(n2, pk_lin(a.to_q)[0], None, B, N, heads, d, 1)
+        o = attend_qkv(q, kv[0], kv[1], Nq=N, Nk=context.shape[1], scale=a.scale)
+    else:
+        q = project_heads(n2, pk_lin(a.to_q)[0], None, B, N, heads, d)
+        o = attend(q, kv[0], kv[1], B=B, heads=heads, Nq=N, Nk=context.shape[1], scale=a.scale)
     w, bb = pk_lin(a.to_out[0])
     t = nv.linear(o.reshape(B * N, inner), w, bb, residual=t)
     # --- GEGLU feed-forward (attention.py:305)

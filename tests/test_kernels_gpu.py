@@ -288,3 +288,33 @@ def test_flash_attention(nv, B, heads, Nq, Nk, d):
     close(o_unfused, ref, rtol=6e-3, atol=2e-3)
     # flash path: packed-half2 exp (MUFU.EX2.F16) -> probabilities carry ~2^-11 relative error
     close(o_flash, ref, rtol=8e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("B,heads,N,Nk,d,cross", [(2, 8, 4096, 4096, 40, False), (2, 8, 4096, 148, 40, True),
+                                                  (2, 8, 1024, 1024, 80, False), (1, 8, 256, 256, 160, False),
+                                                  (1, 4, 100, 77, 40, True), (1, 2, 300, 300, 64, False),
+                                                  (2, 8, 1024, 148, 80, True), (1, 8, 64, 148, 160, True)])
+def test_flash_attention_v2_fused_qkv(nv, B, heads, N, Nk, d, cross):
+    """v2: one fused q|k|v (or k|v) projection GEMM -> strided views -> flash kernel with MN-major V."""
+    from pfd_b200 import attention as att
+    C = heads * d
+    x = rnd(B * N, C, scale=1.0)
+    wq, wk, wv = (rnd(C, C, scale=C ** -0.5, seed=s) for s in (4, 5, 6))
+    scale = d ** -0.5
+    if cross:
+        ctx = rnd(B * Nk, C, scale=1.0, seed=3)
+        q = att.project_heads_fused(x, wq, None, B, N, heads, d, 1)
+        kv = att.project_heads_fused(ctx, torch.cat([wk, wv], 0).contiguous(), None, B, Nk, heads, d, 2)
+        k, v = kv[:, :heads], kv[:, heads:]
+    else:
+        ctx = x
+        qkv = att.project_heads_fused(x, torch.cat([wq, wk, wv], 0).contiguous(), None, B, N, heads, d, 3)
+        q, k, v = qkv[:, :heads], qkv[:, heads:2 * heads], qkv[:, 2 * heads:]
+    o = att.attend_qkv(q, k, v, Nq=N, Nk=Nk, scale=scale)
+    torch.cuda.synchronize()
+    qf = (x.float() @ wq.float().t()).half().float().reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    kf = (ctx.float() @ wk.float().t()).half().float().reshape(B, Nk, heads, d).permute(0, 2, 1, 3)
+    vf = (ctx.float() @ wv.float().t()).half().float().reshape(B, Nk, heads, d).permute(0, 2, 1, 3)
+    sc = (torch.matmul(qf, kf.transpose(-1, -2)).half().float() * scale).half().float()
+    ref = torch.matmul(torch.softmax(sc, -1), vf).permute(0, 2, 1, 3).reshape(B, N, C)
+    close(o, ref, rtol=8e-3, atol=4e-3)
