@@ -108,11 +108,12 @@ PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d);
  *   224-229, 2732-2734), attention.py:83-84 (eps 1e-6), autokl_modules.py:33-39,
  *   seecoder.py:359,383.
  * ws: scratch of at least NB*groups*16 bytes (fp64 sum / sum-of-squares per (image, group)),
- *     16-byte aligned; zeroed by the call.
+ *     16-byte aligned.  zero_ws != 0: the call zeroes it first (one extra memset node); zero_ws == 0: the
+ *     caller guarantees it is already zero (e.g. one bulk memset of many slots per network evaluation).
  */
 PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, int32_t NB,
                       int64_t HW, int32_t groups, const void* gamma, const void* beta, float eps,
-                      int32_t silu, void* out, float* ws, void* stream);
+                      int32_t silu, void* out, float* ws, int32_t zero_ws, void* stream);
 
 /* LayerNorm over the last dim of [rows, C] fp16 (attention.py:294-296, swin.py norms, seecoder.py norms).
  * Optional fused residual: out = LN(x + res) (post-norm layers of seecoder.py:85-90,135-136). */

@@ -169,6 +169,7 @@ class AutoencoderKL(nn.Module):
         divided by the latent scale unless `pre_scale` carries 1/scale).  Returns NCHW fp16 in [0,1]."""
         dec = self.decoder
         B, Cz, H, W = z.shape
+        nv.gn_reset()
         zc = nv.nchw_to_nhwc(z if z.dtype == torch.float32 else z.to(torch.float16), cpad=8)
         wq, bq = pk_lin(self.post_quant_conv)                              # [8, 8] zero-padded 4x4
         h = nv.linear(zc.reshape(B * H * W, 8), wq, bq, alpha=pre_scale).reshape(B, H, W, 8)

@@ -118,6 +118,7 @@ class ControlNet(nn.Module):
 
     def forward(self, x, hint, timesteps, context, kv=None, hint_feat=None, **kwargs) -> List[torch.Tensor]:
         """controlnet.py:302-324.  x NCHW latents; returns 13 channel-last residuals."""
+        nv.gn_reset()
         x = x.to(torch.float16)
         context = context.to(torch.float16).contiguous()
         silu_emb = time_embed_silu(self.time_embed, timesteps, self.model_channels)

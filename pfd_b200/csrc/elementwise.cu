@@ -607,7 +607,7 @@ using namespace pfd;
 
 extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, int32_t NB,
                                  int64_t HW, int32_t groups, const void* gamma, const void* beta,
-                                 float eps, int32_t silu, void* out, float* ws, void* stream) {
+                                 float eps, int32_t silu, void* out, float* ws, int32_t zero_ws, void* stream) {
   const int C = c1 + (x2 ? c2 : 0);
   if (!x2) c2 = 0;
   if (groups <= 0 || groups > GN_MAX_GROUPS || C % groups) return set_error("pfd_groupnorm_f16: C=%d groups=%d", C, groups);
@@ -615,7 +615,7 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   if (!ws) return set_error("pfd_groupnorm_f16: workspace required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* dws = reinterpret_cast<double*>(ws);
-  cudaMemsetAsync(dws, 0, sizeof(double) * 2 * NB * groups, st);
+  if (zero_ws) cudaMemsetAsync(dws, 0, sizeof(double) * 2 * NB * groups, st);
   const int vecs = C / 8;
   // block = largest multiple of vecs that fits 256 threads (or 320 for C = 2560); wide rows fall back to 256
   int threads = vecs <= 320 ? (vecs <= 256 ? (256 / vecs) * vecs : vecs) : 256;

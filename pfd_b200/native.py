@@ -81,7 +81,7 @@ def load() -> ctypes.CDLL:
     lib.pfd_launch_count.restype = c_int64
     lib.pfd_gemm_f16.argtypes = [POINTER(GemmDesc)]
     lib.pfd_groupnorm_f16.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int64, c_int32,
-                                      c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p, c_void_p]
+                                      c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p, c_int32, c_void_p]
     lib.pfd_layernorm_f16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_float,
                                       c_void_p, c_void_p]
     lib.pfd_softmax_f16.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int64, c_float, c_void_p,
@@ -284,16 +284,29 @@ def bmm_nt(a: torch.Tensor, b: torch.Tensor, *, out: torch.Tensor, so, ndiv: int
 # --------------------------------------------------------------------------------------------
 # normalisation / softmax / misc
 # --------------------------------------------------------------------------------------------
-_gn_ws = {}
+# GroupNorm statistics scratch: a ring of pre-zeroed slots per (device, stream).  `gn_reset()` zeroes the
+# whole ring with ONE memset (called at the start of every network evaluation); each groupnorm() call then
+# takes the next slot without a memset of its own.  If the ring is exhausted the call zeroes its slot itself.
+_GN_SLOT_BYTES = 64 * 32 * 16          # up to 64 images x 32 groups x (sum, sumsq) fp64
+_GN_SLOTS = 256
+_gn_rings = {}
 
 
-def _ws(device, nbytes: int) -> torch.Tensor:
-    key = (str(device), torch.cuda.current_stream().cuda_stream)
-    t = _gn_ws.get(key)
-    if t is None or t.numel() < nbytes:
-        t = torch.empty(max(nbytes, 1 << 16), device=device, dtype=torch.uint8)
-        _gn_ws[key] = t
-    return t
+def _gn_ring():
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    ring = _gn_rings.get(key)
+    if ring is None:
+        buf = torch.zeros(_GN_SLOT_BYTES * _GN_SLOTS, device="cuda", dtype=torch.uint8)
+        ring = {"buf": buf, "next": _GN_SLOTS}      # exhausted until the first gn_reset()
+        _gn_rings[key] = ring
+    return ring
+
+
+def gn_reset() -> None:
+    """Zero all GroupNorm scratch slots of the current stream (one memset) and rewind the ring."""
+    ring = _gn_ring()
+    ring["buf"].zero_()
+    ring["next"] = 0
 
 
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, silu: bool,
@@ -304,9 +317,18 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     C2 = x2.shape[3] if x2 is not None else 0
     if out is None:
         out = torch.empty((NB, H, W, C1 + C2), device=x.device, dtype=torch.float16)
-    ws = _ws(x.device, NB * groups * 16)
+    ring = _gn_ring()
+    need = NB * groups * 16
+    if ring["next"] < _GN_SLOTS and need <= _GN_SLOT_BYTES:
+        ws_ptr, zero = ring["buf"].data_ptr() + ring["next"] * _GN_SLOT_BYTES, 0
+        ring["next"] += 1
+    else:
+        if need > _GN_SLOT_BYTES * _GN_SLOTS:
+            raise RuntimeError("groupnorm: batch too large for the statistics scratch")
+        ws_ptr, zero = ring["buf"].data_ptr(), 1
+        ring["next"] = _GN_SLOTS                    # slot 0 is dirty now: force self-zeroing until the next reset
     _check(load().pfd_groupnorm_f16(x.data_ptr(), C1, _p(x2), C2, NB, H * W, groups, gamma.data_ptr(),
-                                    beta.data_ptr(), eps, int(silu), out.data_ptr(), ws.data_ptr(),
+                                    beta.data_ptr(), eps, int(silu), out.data_ptr(), ws_ptr, zero,
                                     stream_ptr()), "pfd_groupnorm_f16")
     return out
 

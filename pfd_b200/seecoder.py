@@ -75,6 +75,7 @@ class Decoder(nn.Module):
     def forward(self, features: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """features: channel-last [1, h, w, C_tag] -> channel-last [1, h, w, trans_dim] per tag."""
         E = self.trans_dim
+        nv.gn_reset()                                                   # GroupNorm scratch ring (native.groupnorm)
         tags = self.trans_tags[::-1]                                    # res5, res4, res3 (seecoder.py:397)
         bs = features[tags[0]].shape[0]
         if bs != 1:

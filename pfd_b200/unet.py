@@ -376,6 +376,7 @@ class UNetModel2D_Next(nn.Module):
         x = x.to(torch.float16)
         context = context.to(torch.float16).contiguous()
         B = x.shape[0]
+        nv.gn_reset()
         silu_emb = time_embed_silu(self.time_embed, timesteps, self.model_channels)
         rbs = [i for i, blk in enumerate(self.data_blocks) if isinstance(blk[0], ResBlock)]
         emb_list = batched_emb_layers(self, [self.data_blocks[i][0] for i in rbs], silu_emb)
