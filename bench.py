@@ -213,7 +213,7 @@ def gemm_roofline_pass(net, sampler_cls, cond, uncond, batch, L):
     torch.cuda.synchronize()
 
     def graph_ms(skip=()):
-        skip = tuple(skip) + (("flash_attn_qkv",) if "flash_attn" in skip else ())
+        skip = tuple(skip) + (("flash_attn_qkv", "flash_attn_strided") if "flash_attn" in skip else ())
         saved = {k: getattr(nv, k) for k in skip}
         try:
             if "gemm_raw" in skip:
@@ -221,6 +221,7 @@ def gemm_roofline_pass(net, sampler_cls, cond, uncond, batch, L):
             if "flash_attn" in skip:
                 nv.flash_attn = lambda q, k, vt, **kw: kw["out"]
                 nv.flash_attn_qkv = lambda q, k, v, **kw: kw["out"]
+                nv.flash_attn_strided = lambda q, k, vt, **kw: kw["out"]
             if "groupnorm" in skip:
                 def gn(x_, g_, b_, eps_, silu=False, x2=None, groups=32, out=None):
                     if out is not None:

@@ -194,6 +194,15 @@ PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const void* vt, voi
                                int32_t k_rows, float scale, int64_t vt_pitch, int64_t o_sb, int64_t o_sq,
                                int32_t reserved, void* stream);
 
+/* Same kernel with arbitrary 4-D strided operands: q, k as [B, heads, N, d] views and vt as [B, heads, d, Nk]
+ * views, strides {batch, head, row} in elements (rows contiguous).  Lets a fused q|k projection GEMM and a
+ * "swapped" V^T = Wv . X^T GEMM ([C, B*N] row-major) feed the kernel without any re-layout. */
+PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, const void* vt, void* out, int32_t B,
+                                       int32_t heads, int32_t Nq, int32_t Nk, int32_t d,
+                                       const int64_t* q_strides, const int64_t* k_strides,
+                                       const int64_t* vt_strides, float scale, int64_t o_sb, int64_t o_sq,
+                                       void* stream);
+
 /*
  * Flash attention v2: q / k / v are 4-D strided views [B, heads, N, d] (strides {batch, head, row} in elements,
  * d contiguous), so one projection GEMM can emit q|k|v (or k|v) side by side; V is read in its natural

@@ -23,7 +23,9 @@ from . import native as nv
 # QK^T GEMM -> softmax -> PV GEMM pipeline (still all pfd_b200 kernels) — used by tests to cross-check.
 USE_FLASH = True
 # v2: fused q|k|v projection GEMM + strided / MN-major-V flash kernel (pfd_flash_attn_qkv_f16)
-USE_FLASH_V2 = True
+USE_FLASH_V2 = False
+# fused q|k projection + V^T produced by a "swapped" GEMM (Wv . X^T), consumed by the v1 kernel through strided views
+USE_FUSED_QK = True
 
 
 def ceil8(n: int) -> int:
@@ -104,3 +106,14 @@ def attend_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, Nq: int, Nk
     if out is None:
         out = torch.empty((B, Nq, heads * d), device=q.device, dtype=torch.float16)
     return nv.flash_attn_qkv(q, k, v, Nq=Nq, Nk=Nk, scale=scale, out=out)
+
+
+def project_vt_swapped(x2d: torch.Tensor, wv: torch.Tensor, B: int, N: int, heads: int, d: int) -> torch.Tensor:
+    """V^T for all batches with ONE vector-store GEMM: out[C, B*N] = Wv[C, Cin] @ x2d[B*N, Cin]^T (the weight is the
+    A operand, the tokens are the K-major B operand).  Returns the strided view [B, heads, d, N]."""
+    C, Cin = wv.shape
+    T = x2d.shape[0]                                   # B*N tokens (N % 8 == 0 for the UNet self-attention)
+    out = torch.empty((C, T), device=x2d.device, dtype=torch.float16)
+    nv.gemm_raw([(wv, 1, Cin, (wv.stride(0), wv.stride(0) * C, wv.stride(0) * C))], in_w=C, in_h=1, stride=1, W=C,
+                H=1, NB=1, w=x2d, N=T, K=x2d.stride(0), out=out, so=(0, 0, 0, T, 0, 1))
+    return out.as_strided((B, heads, d, N), (N, d * T, T, 1))

@@ -99,6 +99,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * FA_BQ;
   const int bh = blockIdx.y;
+  const int hb = bh % p.heads, bb = bh / p.heads;
   const int nblk = p.nblk;
 
   if (warp == 0 && lane == 0) {
@@ -142,14 +143,14 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(bar_q, Cfg::Q_BYTES);
-      for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + c * FA_BQ * 128, &p.tmQ, bar_q, c * 64, q0, bh);
+      for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * FA_BQ * 128, &p.tmQ, bar_q, c * 64, q0, hb, bb);
       for (int j = 0; j < nblk; ++j) {
         const int st = j & 1, u = j >> 1;
         if (u >= 1) mbar_wait(bar_kv_empty(st), (u - 1) & 1);
         mbar_expect_tx(bar_kv_full(st), Cfg::K_BYTES + d * 128);
         for (int c = 0; c < DCH; ++c)
-          tma_load_3d(sK + st * Cfg::K_BYTES + c * FA_BKV * 128, &p.tmK, bar_kv_full(st), c * 64, j * FA_BKV, bh);
-        tma_load_3d(sV + st * V_BYTES, &p.tmV, bar_kv_full(st), j * FA_BKV, 0, bh);
+          tma_load_4d(sK + st * Cfg::K_BYTES + c * FA_BKV * 128, &p.tmK, bar_kv_full(st), c * 64, j * FA_BKV, hb, bb);
+        tma_load_4d(sV + st * V_BYTES, &p.tmV, bar_kv_full(st), j * FA_BKV, 0, hb, bb);
       }
     }
   } else if (warp == 1) {
@@ -333,8 +334,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode3d(CUtensorMap* m, const void* ptr, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
-                    cuuint64_t s1_bytes, cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1, const char* what) {
+static int encode4d(CUtensorMap* m, const void* ptr, cuuint64_t inner, cuuint64_t rows, cuuint64_t heads,
+                    cuuint64_t B, long long sr, long long sh, long long sb, cuuint32_t box_rows, const char* what) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* fp = nullptr;
@@ -344,17 +345,17 @@ static int encode3d(CUtensorMap* m, const void* ptr, cuuint64_t d0, cuuint64_t d
       return set_error("cuTensorMapEncodeTiled entry point unavailable");
     fn = reinterpret_cast<EncodeTiledFn>(fp);
   }
-  cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {s1_bytes, s2_bytes};
-  cuuint32_t box[3] = {b0, b1, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+  cuuint64_t dims[4] = {inner, rows, heads, B};
+  cuuint64_t strides[3] = {(cuuint64_t)sr * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return set_error("flash attention tensor map (%s) encode failed: CUresult %d dims[%llu,%llu,%llu] strides[%llu,%llu] box[%u,%u]",
-                     what, (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
-                     (unsigned long long)s1_bytes, (unsigned long long)s2_bytes, b0, b1);
+    return set_error("flash attention tensor map (%s) encode failed: CUresult %d dims[%llu,%llu,%llu,%llu] strides[%lld,%lld,%lld]",
+                     what, (int)r, (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)heads,
+                     (unsigned long long)B, sr, sh, sb);
   return 0;
 }
 
@@ -377,28 +378,42 @@ static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t st) {
 
 using namespace pfd;
 
-extern "C" PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const void* vt, void* out, int32_t B,
-                                          int32_t heads, int32_t Nq, int32_t Nk, int32_t d, int32_t q_rows,
-                                          int32_t k_rows, float scale, int64_t vt_pitch, int64_t o_sb,
-                                          int64_t o_sq, int32_t reserved, void* stream) {
-  (void)reserved;
+extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, const void* vt, void* out,
+                                                  int32_t B, int32_t heads, int32_t Nq, int32_t Nk, int32_t d,
+                                                  const int64_t* q_strides, const int64_t* k_strides,
+                                                  const int64_t* vt_strides, float scale, int64_t o_sb,
+                                                  int64_t o_sq, void* stream) {
   if (d % 8 || d <= 0 || d > 192) return set_error("pfd_flash_attn_f16: head dim %d unsupported", d);
   if (Nq <= 0 || Nk <= 0) return set_error("pfd_flash_attn_f16: empty problem");
-  if (vt_pitch % 8) return set_error("pfd_flash_attn_f16: V^T pitch must be a multiple of 8");
+  for (int i = 0; i < 3; ++i)
+    if (q_strides[i] % 8 || k_strides[i] % 8 || vt_strides[i] % 8)
+      return set_error("pfd_flash_attn_f16: strides must be multiples of 8 elements");
   FlashParams p;
   memset(&p, 0, sizeof(p));
-  const long long BH = (long long)B * heads;
-  if (int rc = encode3d(&p.tmQ, q, d, Nq, BH, (cuuint64_t)d * 2, (cuuint64_t)q_rows * d * 2, 64, FA_BQ, "Q")) return rc;
-  if (int rc = encode3d(&p.tmK, k, d, Nk, BH, (cuuint64_t)d * 2, (cuuint64_t)k_rows * d * 2, 64, FA_BKV, "K")) return rc;
-  if (int rc = encode3d(&p.tmV, vt, Nk, d, BH, (cuuint64_t)vt_pitch * 2, (cuuint64_t)d * vt_pitch * 2, 64, (cuuint32_t)d, "V^T")) return rc;
+  // strides = {batch, head, row} in elements; q/k rows run over d, vt rows (one per channel) run over the keys
+  if (int rc = encode4d(&p.tmQ, q, d, Nq, heads, B, q_strides[2], q_strides[1], q_strides[0], FA_BQ, "Q")) return rc;
+  if (int rc = encode4d(&p.tmK, k, d, Nk, heads, B, k_strides[2], k_strides[1], k_strides[0], FA_BKV, "K")) return rc;
+  if (int rc = encode4d(&p.tmV, vt, Nk, d, heads, B, vt_strides[2], vt_strides[1], vt_strides[0], (cuuint32_t)d, "V^T")) return rc;
   p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.d = d;
   p.nblk = (Nk + FA_BKV - 1) / FA_BKV;
   p.scale = scale;
   p.out = static_cast<__half*>(out);
   p.o_sb = o_sb; p.o_sq = o_sq; p.o_sh = d;
-  dim3 grid((Nq + FA_BQ - 1) / FA_BQ, (unsigned)BH);
+  dim3 grid((Nq + FA_BQ - 1) / FA_BQ, (unsigned)((long long)B * heads));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d <= 64) return launch_flash<1>(p, grid, st);
   if (d <= 128) return launch_flash<2>(p, grid, st);
   return launch_flash<3>(p, grid, st);
+}
+
+extern "C" PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const void* vt, void* out, int32_t B,
+                                          int32_t heads, int32_t Nq, int32_t Nk, int32_t d, int32_t q_rows,
+                                          int32_t k_rows, float scale, int64_t vt_pitch, int64_t o_sb,
+                                          int64_t o_sq, int32_t reserved, void* stream) {
+  (void)reserved;
+  // packed layouts: q [B*heads, q_rows, d], k [B*heads, k_rows, d], vt [B*heads, d, vt_pitch]
+  const int64_t qs[3] = {(int64_t)heads * q_rows * d, (int64_t)q_rows * d, d};
+  const int64_t ks[3] = {(int64_t)heads * k_rows * d, (int64_t)k_rows * d, d};
+  const int64_t vs[3] = {(int64_t)heads * d * vt_pitch, (int64_t)d * vt_pitch, vt_pitch};
+  return pfd_flash_attn_strided_f16(q, k, vt, out, B, heads, Nq, Nk, d, qs, ks, vs, scale, o_sb, o_sq, stream);
 }

@@ -27,7 +27,7 @@ EXPORTS = [
     "pfd_nchw_to_nhwc_f16", "pfd_nhwc_to_nchw_f16", "pfd_im2col3x3_f16", "pfd_axpby_f16",
     "pfd_add_rowvec_f16", "pfd_ddim_step_f16", "pfd_window_gather_f16", "pfd_window_scatter_f16",
     "pfd_patch_merge_gather_f16", "pfd_patchify_f16", "pfd_flash_attn_f16",
-    "pfd_flash_attn_qkv_f16",
+    "pfd_flash_attn_qkv_f16", "pfd_flash_attn_strided_f16",
 ]
 
 
@@ -113,6 +113,7 @@ def load() -> ctypes.CDLL:
     lib.pfd_flash_attn_qkv_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                            c_int32, c_int32, POINTER(c_int64), POINTER(c_int64),
                                            POINTER(c_int64), c_float, c_int64, c_int64, c_void_p]
+    lib.pfd_flash_attn_strided_f16.argtypes = list(lib.pfd_flash_attn_qkv_f16.argtypes)
     for name in EXPORTS:
         if hasattr(lib, name) and name not in ("pfd_version", "pfd_last_error", "pfd_launch_count"):
             getattr(lib, name).restype = c_int32
@@ -486,4 +487,16 @@ def flash_attn_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, Nq: int
     _check(load().pfd_flash_attn_qkv_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nk,
                                          d, st(q), st(k), st(v), scale, out.stride(0), out.stride(1), stream_ptr()),
            "pfd_flash_attn_qkv_f16")
+    return out
+
+
+def flash_attn_strided(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, Nq: int, Nk: int, scale: float,
+                       out: torch.Tensor) -> torch.Tensor:
+    """pfd_flash_attn_strided_f16: q, k strided views [B, heads, N(p), d]; vt strided view [B, heads, d, Nk(p)]
+    (rows contiguous); out [B, Nq, heads*d]."""
+    B, heads, _, d = q.shape
+    st = lambda t: (c_int64 * 3)(t.stride(0), t.stride(1), t.stride(2))
+    _check(load().pfd_flash_attn_strided_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Nq,
+                                             Nk, d, st(q), st(k), st(vt), scale, out.stride(0), out.stride(1),
+                                             stream_ptr()), "pfd_flash_attn_strided_f16")
     return out

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import native as nv
 from . import attention as att
-from .attention import attend, attend_qkv, ceil8, project_heads, project_heads_fused
+from .attention import attend, attend_qkv, ceil8, project_heads, project_heads_fused, project_vt_swapped
 from .modules import (Conv2d, GroupNorm, IndexedSequential, LayerNorm, Linear, cached, pk_conv3,
                       pk_conv3_small, pk_lin, pk_mat, pk_norm)
 
@@ -190,6 +190,11 @@ def run_spatial_transformer(st: SpatialTransformer, x: torch.Tensor, context: to
     if att.USE_FLASH_V2:
         qkv = project_heads_fused(n1, _cat_weights(a, "qkv_cat", [a.to_q, a.to_k, a.to_v]), None, B, N, heads, d, 3)
         o = attend_qkv(qkv[:, :heads], qkv[:, heads:2 * heads], qkv[:, 2 * heads:], Nq=N, Nk=N, scale=a.scale)
+    elif att.USE_FUSED_QK and N % 8 == 0:
+        qk = project_heads_fused(n1, _cat_weights(a, "qk_cat", [a.to_q, a.to_k]), None, B, N, heads, d, 2)
+        vt4 = project_vt_swapped(n1, pk_lin(a.to_v)[0], B, N, heads, d)
+        o = nv.flash_attn_strided(qk[:, :heads], qk[:, heads:], vt4, Nq=N, Nk=N, scale=a.scale,
+                                  out=torch.empty((B, N, inner), device=t.device, dtype=torch.float16))
     else:
         q = project_heads(n1, pk_lin(a.to_q)[0], None, B, N, heads, d)
         k = project_heads(n1, pk_lin(a.to_k)[0], None, B, N, heads, d)

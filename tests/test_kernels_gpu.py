@@ -318,3 +318,25 @@ def test_flash_attention_v2_fused_qkv(nv, B, heads, N, Nk, d, cross):
     sc = (torch.matmul(qf, kf.transpose(-1, -2)).half().float() * scale).half().float()
     ref = torch.matmul(torch.softmax(sc, -1), vf).permute(0, 2, 1, 3).reshape(B, N, C)
     close(o, ref, rtol=8e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("B,heads,N,d", [(2, 8, 4096, 40), (2, 8, 1024, 80), (1, 8, 256, 160), (3, 4, 64, 40)])
+def test_flash_attention_fused_qk_swapped_vt(nv, B, heads, N, d):
+    """UNet self-attention path: fused q|k projection GEMM + V^T from the swapped GEMM (Wv . X^T) feeding
+    the v1 flash kernel through strided views."""
+    from pfd_b200 import attention as att
+    C = heads * d
+    x = rnd(B * N, C, scale=1.0)
+    wq, wk, wv = (rnd(C, C, scale=C ** -0.5, seed=s) for s in (4, 5, 6))
+    scale = d ** -0.5
+    qk = att.project_heads_fused(x, torch.cat([wq, wk], 0).contiguous(), None, B, N, heads, d, 2)
+    vt4 = att.project_vt_swapped(x, wv, B, N, heads, d)
+    o = torch.empty((B, N, C), device="cuda", dtype=torch.float16)
+    nv.flash_attn_strided(qk[:, :heads], qk[:, heads:], vt4, Nq=N, Nk=N, scale=scale, out=o)
+    torch.cuda.synchronize()
+    qf = (x.float() @ wq.float().t()).half().float().reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    kf = (x.float() @ wk.float().t()).half().float().reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    vf = (x.float() @ wv.float().t()).half().float().reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    sc = (torch.matmul(qf, kf.transpose(-1, -2)).half().float() * scale).half().float()
+    ref = torch.matmul(torch.softmax(sc, -1), vf).permute(0, 2, 1, 3).reshape(B, N, C)
+    close(o, ref, rtol=8e-3, atol=4e-3)
