@@ -61,8 +61,11 @@ struct FlashCfg {
   // S accumulators in TMEM: one for d <= 64 (64 + 48 columns -> 128-column allocation, ~60 KB smem ->
   // three CTAs per SM overlap each other's TMEM-load / MUFU / smem / MMA phases), two otherwise
   static constexpr int NSB = DCH == 1 ? 1 : 2;
+  // K/V smem stages: one for d <= 64 (46 KB per CTA -> FOUR co-resident CTAs hide each other's TMA latency),
+  // two otherwise
+  static constexpr int NKV = DCH == 1 ? 1 : 2;
   // V^T stage = dN rows x 128 B (dN = ceil16(d + 1), runtime) so d=80 still fits two CTAs per SM
-  static int smem_bytes(int dN) { return Q_BYTES + 2 * (K_BYTES + dN * 128) + NPB * P_BYTES + 1024 + 128; }
+  static int smem_bytes(int dN) { return Q_BYTES + NKV * (K_BYTES + dN * 128) + NPB * P_BYTES + 1024 + 128; }
 };
 
 template <int DCH>
@@ -80,10 +83,10 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   const uint32_t tmem_cols = need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u);
   const uint32_t sQ = base;
   const uint32_t sK = sQ + Cfg::Q_BYTES;                  // [2][K_BYTES]
-  const uint32_t sV = sK + 2 * Cfg::K_BYTES;              // [2][V_BYTES]
-  const uint32_t sP = sV + 2 * V_BYTES;
+  const uint32_t sV = sK + Cfg::NKV * Cfg::K_BYTES;       // [NKV][V_BYTES]
+  const uint32_t sP = sV + Cfg::NKV * V_BYTES;
   const uint32_t bars = sP + Cfg::NPB * Cfg::P_BYTES;
-  uint8_t* gP = gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES;
+  uint8_t* gP = gbase + Cfg::Q_BYTES + Cfg::NKV * Cfg::K_BYTES + Cfg::NKV * V_BYTES;
   const uint32_t bar_q = bars;
   auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
   auto bar_kv_empty = [&](int s) { return bars + 8u * (3 + s); };
@@ -93,7 +96,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   const uint32_t bar_pv_done = bars + 8u * 10;
   const uint32_t tmem_slot = bars + 8u * 11;
   volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(
-      gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES + 2 * V_BYTES + Cfg::NPB * Cfg::P_BYTES + 8 * 11);
+      gbase + Cfg::Q_BYTES + Cfg::NKV * Cfg::K_BYTES + Cfg::NKV * V_BYTES + Cfg::NPB * Cfg::P_BYTES + 8 * 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,10 +125,10 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   if (warp == 2) tmem_alloc_rt(tmem_slot, tmem_cols);
   if (warp >= 2) {
     // rows d..dN-1 of both V^T stages are never written by TMA (its box has d rows): row d = ones, rest = 0
-    uint8_t* gV = gbase + Cfg::Q_BYTES + 2 * Cfg::K_BYTES;
+    uint8_t* gV = gbase + Cfg::Q_BYTES + Cfg::NKV * Cfg::K_BYTES;
     const int t = threadIdx.x - 64;
     const int per_stage = (dN - d) * 8;               // 16-byte granules
-    for (int i = t; i < 2 * per_stage; i += 128) {
+    for (int i = t; i < Cfg::NKV * per_stage; i += 128) {
       const int st = i / per_stage, g = i % per_stage;
       const uint32_t word = (g < 8) ? 0x3C003C00u : 0u;
       *reinterpret_cast<uint4*>(gV + st * V_BYTES + d * 128 + g * 16) = make_uint4(word, word, word, word);
@@ -145,7 +148,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       mbar_expect_tx(bar_q, Cfg::Q_BYTES);
       for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * FA_BQ * 128, &p.tmQ, bar_q, c * 64, q0, hb, bb);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1, u = j >> 1;
+        const int st = j % Cfg::NKV, u = j / Cfg::NKV;
         if (u >= 1) mbar_wait(bar_kv_empty(st), (u - 1) & 1);
         mbar_expect_tx(bar_kv_full(st), Cfg::K_BYTES + d * 128);
         for (int c = 0; c < DCH; ++c)
@@ -158,7 +161,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       const uint32_t idesc_s = make_idesc_f16(FA_BKV);
       const uint32_t idesc_o = make_idesc_f16((uint32_t)dN);
       auto issue_S = [&](int j) {
-        const int st = j & 1;
+        const int st = j % Cfg::NKV;
         const int sb = j % Cfg::NSB;
         const uint32_t tS = tmem_base + sb * FA_BKV;
         bool first = true;
@@ -180,17 +183,22 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       tc_fence_after();
       issue_S(0);
       for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          const int st = (j + 1) & 1, u = (j + 1) >> 1;
-          const int sb = (j + 1) % Cfg::NSB, us = (j + 1) / Cfg::NSB;
-          mbar_wait(bar_kv_full(st), u & 1);
-          if (us >= 1) mbar_wait(bar_s_free(sb), (us - 1) & 1);
-          tc_fence_after();
-          issue_S(j + 1);
-        }
+        auto next_S = [&]() {
+          if (j + 1 < nblk) {
+            const int st = (j + 1) % Cfg::NKV, u = (j + 1) / Cfg::NKV;
+            const int sb = (j + 1) % Cfg::NSB, us = (j + 1) / Cfg::NSB;
+            mbar_wait(bar_kv_full(st), u & 1);
+            if (us >= 1) mbar_wait(bar_s_free(sb), (us - 1) & 1);
+            tc_fence_after();
+            issue_S(j + 1);
+          }
+        };
+        // two K/V stages: QK^T of block j+1 is issued before PV of block j (overlaps the softmax of j);
+        // one stage: K_{j+1} can only land after PV_j released the stage, so PV_j goes first
+        if (Cfg::NKV > 1) next_S();
         mbar_wait(bar_p_ready, j & 1);
         tc_fence_after();
-        const int st = j & 1;
+        const int st = j % Cfg::NKV;
         const uint64_t ad = make_sw128_kmajor_desc(sP + (Cfg::NPB == 2 ? (j & 1) * Cfg::P_BYTES : 0));
         const uint64_t bd = make_sw128_kmajor_desc(sV + st * V_BYTES);
 #pragma unroll
@@ -198,6 +206,7 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
           umma_f16(tmem_O, ad + 2u * s, bd + 2u * s, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
         umma_commit(bar_kv_empty(st));
         umma_commit(bar_pv_done);
+        if (Cfg::NKV == 1) next_S();
       }
     }
   } else {
