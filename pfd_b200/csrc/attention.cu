@@ -61,9 +61,9 @@ struct FlashCfg {
   // S accumulators in TMEM: one for d <= 64 (64 + 48 columns -> 128-column allocation, ~60 KB smem ->
   // three CTAs per SM overlap each other's TMEM-load / MUFU / smem / MMA phases), two otherwise
   static constexpr int NSB = DCH == 1 ? 1 : 2;
-  // K/V smem stages: one for d <= 64 (46 KB per CTA -> FOUR co-resident CTAs hide each other's TMA latency),
-  // two otherwise
-  static constexpr int NKV = DCH == 1 ? 1 : 2;
+  // K/V smem stages
+  //
+  static constexpr int NKV = 2;   // (1 stage -> 4 CTAs/SM was measured 55% slower: intra-CTA QK^T/softmax overlap matters more)
   // V^T stage = dN rows x 128 B (dN = ceil16(d + 1), runtime) so d=80 still fits two CTAs per SM
   static int smem_bytes(int dN) { return Q_BYTES + NKV * (K_BYTES + dN * 128) + NPB * P_BYTES + 1024 + 128; }
 };
