@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_eager"])
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--ddim-steps", type=int, default=50)
@@ -376,6 +376,47 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_torch_eager(args):
+    """Context number (not a contract arm): the reference ALGORITHM as plain PyTorch eager fp16 on the same
+    GPU — the oracle port with its state dict moved to CUDA, i.e. what the reference repo would run on a B200
+    (cuDNN / cuBLAS / ATen kernels, materialised attention, per-step host syncs).  Same workload, same metric."""
+    import torch
+    from oracle import pfd_oracle as O
+    net = synth_cpu_state()
+    sd = {k: v.detach().half().cuda() for k, v in net.state_dict().items() if v.dtype.is_floating_point}
+    usd, vsd, ssd = O.sub(sd, "diffuser.image."), O.sub(sd, "vae.image."), O.sub(sd, "ctx.image.")
+    ac = net.alphas_cumprod.half()                                    # net.half() rounds the schedule buffers too
+    B, L, R = args.batch, args.res // 8, args.res
+    img = torch.rand((1, 3, R, R), generator=torch.Generator().manual_seed(100)).half().cuda()
+
+    def request():
+        with torch.no_grad():
+            c = O.seecoder_encode(ssd, img).repeat(B, 1, 1)
+            torch.manual_seed(20)
+            x_T = torch.randn((B, 4, L, L), device="cuda", dtype=torch.float16)
+            x = O.ddim_sample(usd, O.UNET_SD15, ac, steps=args.ddim_steps, x_T=x_T, cond=c,
+                              uncond=torch.zeros_like(c), guidance=2.0)
+            return O.vae_decode(vsd, O.VAE_SD, x)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        request()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        im = request()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    line = {"impl": "torch_eager_port", "metric": METRIC, "value": B * args.steps / (ms / 1000.0), "unit": "images/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "dtype": "fp16", "data": "synthetic",
+            "config": {"workload": f"{R}x{R}, {args.ddim_steps} DDIM steps, CFG 2.0, batch {B}: reference algorithm "
+                                   "(oracle port) in PyTorch eager fp16 on the same GPU"},
+            "output_finite": bool(torch.isfinite(im.float()).all().item())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
@@ -384,6 +425,8 @@ def main():
         sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_eager":
+        run_torch_eager(args)
     else:
         run_ours(args)
 

@@ -104,7 +104,7 @@ def ddim_schedule(alphas_cumprod: torch.Tensor, steps: int, eta: float = 0.0):
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     """diffusion_utils.py:131-151: [cos | sin] of t * exp(-ln(P) * i / half), fp32."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -499,12 +499,12 @@ def swin_forward(sd: SD, cfg, img: torch.Tensor) -> Dict[str, torch.Tensor]:
     x = F.conv2d(img, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=ps)
     Wh, Ww = x.shape[2], x.shape[3]
     x = _ln(x.flatten(2).transpose(1, 2), sd, "patch_embed.norm")
-    rpi = relative_position_index(ws)
+    rpi = relative_position_index(ws).to(x.device)
     outs = {}
     nl = len(cfg["depths"])
     for i in range(nl):
         C = cfg["embed_dim"] * 2 ** i
-        mask = swin_shift_mask(Wh, Ww, ws, ws // 2, x.dtype)
+        mask = swin_shift_mask(Wh, Ww, ws, ws // 2, x.dtype).to(x.device)
         for j in range(cfg["depths"][i]):
             x = swin_block(sd, f"layers.{i}.blocks.{j}.", x, Wh, Ww, ws, 0 if j % 2 == 0 else ws // 2,
                            cfg["num_heads"][i], mask, rpi)
@@ -564,9 +564,9 @@ def ppe_mlp(sd: SD, p: str, x: torch.Tensor, freq_num: int = 20) -> torch.Tensor
     h, w = x.shape[-2:]
     minlen = min(h, w)
     he, we = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
-    he = ((he + 0.5 - h / 2) / minlen * (2 * math.pi)).to(x.dtype)
-    we = ((we + 0.5 - w / 2) / minlen * (2 * math.pi)).to(x.dtype)
-    dim_t = torch.linspace(0, 1, freq_num, dtype=torch.float32)
+    he = ((he + 0.5 - h / 2) / minlen * (2 * math.pi)).to(x.device).to(x.dtype)
+    we = ((we + 0.5 - w / 2) / minlen * (2 * math.pi)).to(x.device).to(x.dtype)
+    dim_t = torch.linspace(0, 1, freq_num, dtype=torch.float32, device=x.device)
     dim_t = (minlen / 2) ** dim_t.to(x.dtype)
     ph, pw = he[:, :, None] * dim_t, we[:, :, None] * dim_t
     pos = torch.cat((ph.sin(), ph.cos(), pw.sin(), pw.cos()), dim=-1)
@@ -623,7 +623,7 @@ def ddim_update(x, e_t, a_t, a_prev, sigma_t, sqrt_one_minus_at):
     torch.full(..., dtype=x.dtype) tensors exactly as in the reference."""
     b = x.shape[0]
     ext = [b] + [1] * (x.dim() - 1)
-    mk = lambda v: torch.full(ext, float(v), dtype=x.dtype)
+    mk = lambda v: torch.full(ext, float(v), dtype=x.dtype, device=x.device)
     a_t, a_prev, sigma_t, s1m = mk(a_t), mk(a_prev), mk(sigma_t), mk(sqrt_one_minus_at)
     pred_x0 = (x - s1m * e_t) / a_t.sqrt()
     dir_xt = (1.0 - a_prev - sigma_t ** 2).sqrt() * e_t
@@ -643,7 +643,7 @@ def ddim_sample(unet_sd: SD, unet_cfg, alphas_cumprod: torch.Tensor, *, steps: i
         if max_evals is not None and i >= max_evals:
             break
         index = total - i - 1
-        t = torch.full((b,), int(step), dtype=torch.long)
+        t = torch.full((b,), int(step), dtype=torch.long, device=x.device)
         if guidance == 1.0 or uncond is None:
             control = controlnet_apply(ctl_sd, ctl_cfg, x, hint, t, cond) if hint is not None else None
             e_t = unet_apply(unet_sd, unet_cfg, x, t, cond, control) * guidance

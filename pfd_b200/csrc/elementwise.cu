@@ -221,6 +221,145 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   }
 }
 
+// Single-pass GroupNorm: each CTA keeps its pixel chunk in shared memory between the statistics phase and
+// the apply phase, so the activation is read from L2/HBM ONCE (the two-kernel version reads it twice) and
+// one launch disappears.  The phases are separated by a per-image arrival counter in global memory; this is
+// only used when every CTA of the grid can be co-resident (host checks with the occupancy API), and the
+// dependent kernel is not allowed to start launching before the barrier has been passed.
+__global__ void __launch_bounds__(320)
+gn_fused_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, long long HW,
+                int groups, const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
+                int silu, double* __restrict__ ws, unsigned int* __restrict__ counter, __half* __restrict__ out,
+                long long pix_per_cta, double inv_cnt) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  extern __shared__ uint4 gn_tile[];
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int vecs = C / 8;
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  long long p1 = p0 + pix_per_cta;
+  if (p1 > HW) p1 = HW;
+  __shared__ float s_sum[GN_MAX_GROUPS];
+  __shared__ float s_sq[GN_MAX_GROUPS];
+  if (threadIdx.x < GN_MAX_GROUPS) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int lanes = blockDim.x / vecs;          // host guarantees lanes >= 1 for this kernel
+  const int v = threadIdx.x % vecs;
+  const int c = v * 8;
+  const long long base = (long long)n * HW;
+  const bool active = threadIdx.x < lanes * vecs;
+  if (active) {
+    float sm[8], sq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[i] = sq[i] = 0.f;
+    long long pix = p0 + threadIdx.x / vecs;
+    for (; pix + 3 * lanes < p1; pix += 4 * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = gn_load(x1, c1, x2, c2, base + pix + k * lanes, c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        gn_tile[(pix + k * lanes - p0) * vecs + v] = u[k];
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sm[i] += f[i];
+          sq[i] += f[i] * f[i];
+        }
+      }
+    }
+    for (; pix < p1; pix += lanes) {
+      const uint4 u = gn_load(x1, c1, x2, c2, base + pix, c);
+      gn_tile[(pix - p0) * vecs + v] = u;
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sm[i] += f[i];
+        sq[i] += f[i] * f[i];
+      }
+    }
+    int g_prev = c / cpg;
+    float as = 0.f, aq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / cpg;
+      if (g != g_prev) {
+        atomicAdd(&s_sum[g_prev], as);
+        atomicAdd(&s_sq[g_prev], aq);
+        as = aq = 0.f;
+        g_prev = g;
+      }
+      as += sm[i];
+      aq += sq[i];
+    }
+    atomicAdd(&s_sum[g_prev], as);
+    atomicAdd(&s_sq[g_prev], aq);
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    atomicAdd(&ws[((long long)n * groups + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
+    atomicAdd(&ws[((long long)n * groups + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  }
+  // ---- per-image barrier over the gridDim.x CTAs of image n
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&counter[n], 1u);
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(&counter[n]) < gridDim.x) {
+      __nanosleep(64);
+      if (++spins > (1u << 22)) asm volatile("trap;");
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!active) return;
+  // ---- apply from shared memory
+  float a8[8], b8[8];
+  {
+    float g8[8], be8[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + c)), g8);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c)), be8);
+    int gprev = -1;
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / cpg;
+      if (g != gprev) {
+        const double m = __ldcg(&ws[((long long)n * groups + g) * 2 + 0]) * inv_cnt;
+        double var = __ldcg(&ws[((long long)n * groups + g) * 2 + 1]) * inv_cnt - m * m;
+        if (var < 0) var = 0;
+        mean = (float)m;
+        rstd = rsqrtf((float)var + eps);
+        gprev = g;
+      }
+      a8[i] = rstd * g8[i];
+      b8[i] = be8[i] - mean * a8[i];
+    }
+  }
+  for (long long pix = p0 + threadIdx.x / vecs; pix < p1; pix += lanes) {
+    float f[8];
+    unpack8(gn_tile[(pix - p0) * vecs + v], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = fmaf(f[i], a8[i], b8[i]);
+      if (silu) {
+        y = rh(y);
+        y = __fdividef(y, 1.f + __expf(-y));
+      }
+      f[i] = y;
+    }
+    *reinterpret_cast<uint4*>(out + (base + pix) * C + c) = pack8(f);
+  }
+}
+
 // ------------------------------------------------------------------------------------ LayerNorm
 // one warp per row; C % 8 == 0; row cached in registers (C <= 8*32*MAXV).
 template <int MAXV>
@@ -593,6 +732,15 @@ __global__ void patchify_kernel(const T* __restrict__ x, int B, int C, int H, in
   }
 }
 
+static inline bool gn_fused_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PFD_GN_TWO_PASS");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static inline int grid_for(long long total, int threads) {
   long long g = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -620,6 +768,37 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   // block = largest multiple of vecs that fits 256 threads (or 320 for C = 2560); wide rows fall back to 256
   int threads = vecs <= 320 ? (vecs <= 256 ? (256 / vecs) * vecs : vecs) : 256;
   if (threads < 64) threads = vecs * ((64 + vecs - 1) / vecs);
+  const double inv_cnt = 1.0 / ((double)HW * (C / groups));
+  // ---- single-pass path (chunk cached in shared memory, per-image arrival barrier) when the whole grid can be
+  //      co-resident; counters live right behind the fp64 sums in the (pre-zeroed) scratch slot
+  if (!zero_ws && vecs <= 320 && gn_fused_enabled()) {
+    const int lanes = threads / vecs;
+    static int max_smem_set = 0;
+    const size_t smem_cap = 96 * 1024;
+    long long ppc_f = (long long)(smem_cap / ((size_t)C * 2));
+    ppc_f = (ppc_f / lanes) * lanes;
+    if (ppc_f > HW) ppc_f = ((HW + lanes - 1) / lanes) * lanes;
+    if (ppc_f >= 4 * lanes) {
+      const size_t smem = (size_t)ppc_f * C * 2;
+      if (!max_smem_set) {
+        cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+        max_smem_set = 1;
+      }
+      int per_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem);
+      // shrink the chunk (more CTAs) while everything still fits, to fill the machine
+      long long chunks_f = (HW + ppc_f - 1) / ppc_f;
+      const long long cap = (long long)per_sm * num_sms();
+      if (per_sm > 0 && chunks_f * NB <= cap) {
+        unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + (size_t)NB * groups * 16);
+        dim3 gridf((unsigned)chunks_f, (unsigned)NB);
+        launch_k(gn_fused_kernel, gridf, dim3(threads), smem, st, static_cast<const __half*>(x1), c1,
+                 static_cast<const __half*>(x2), c2, (long long)HW, groups, static_cast<const __half*>(gamma),
+                 static_cast<const __half*>(beta), eps, silu, dws, counter, static_cast<__half*>(out), ppc_f, inv_cnt);
+        return check_launch("gn_fused");
+      }
+    }
+  }
   // ~3 CTAs per SM, but at least 16 pixels per pixel-lane so the per-CTA setup is amortised
   long long chunks = (3LL * num_sms() + NB - 1) / NB;
   long long ppc = (HW + chunks - 1) / chunks;
@@ -633,7 +812,7 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   launch_k(gn_apply_kernel, dim3(grid), dim3(threads), (size_t)(0), st, static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2, HW,
                                             groups, static_cast<const __half*>(gamma), static_cast<const __half*>(beta),
                                             eps, silu, dws, static_cast<__half*>(out), ppc,
-                                            1.0 / ((double)HW * (C / groups)));
+                                            inv_cnt);
   return check_launch("gn_apply");
 }
 

@@ -288,7 +288,7 @@ def bmm_nt(a: torch.Tensor, b: torch.Tensor, *, out: torch.Tensor, so, ndiv: int
 # GroupNorm statistics scratch: a ring of pre-zeroed slots per (device, stream).  `gn_reset()` zeroes the
 # whole ring with ONE memset (called at the start of every network evaluation); each groupnorm() call then
 # takes the next slot without a memset of its own.  If the ring is exhausted the call zeroes its slot itself.
-_GN_SLOT_BYTES = 64 * 32 * 16          # up to 64 images x 32 groups x (sum, sumsq) fp64
+_GN_SLOT_BYTES = 64 * 32 * 16 + 256    # up to 64 images x 32 groups x (sum, sumsq) fp64 + 64 arrival counters
 _GN_SLOTS = 256
 _gn_rings = {}
 
@@ -319,7 +319,7 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     if out is None:
         out = torch.empty((NB, H, W, C1 + C2), device=x.device, dtype=torch.float16)
     ring = _gn_ring()
-    need = NB * groups * 16
+    need = NB * groups * 16 + NB * 4
     if ring["next"] < _GN_SLOTS and need <= _GN_SLOT_BYTES:
         ws_ptr, zero = ring["buf"].data_ptr() + ring["next"] * _GN_SLOT_BYTES, 0
         ring["next"] += 1

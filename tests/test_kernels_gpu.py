@@ -141,13 +141,17 @@ def test_groupnorm(nv, C1, C2, HW, silu):
     x2 = rnd(NB, side, side, C2, seed=3) if C2 else None
     C = C1 + C2
     gamma, beta = rnd(C, seed=4) + 1.0, rnd(C, seed=5)
-    out = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)
+    out = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)          # scratch ring exhausted -> two-pass kernels
+    nv.gn_reset()
+    out_f = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)        # pre-zeroed slot -> single-pass kernel
+    out_f2 = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)       # next slot
     torch.cuda.synchronize()
     xc = x1 if x2 is None else torch.cat([x1, x2], 3)
     ref = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-5)
     if silu:
         ref = F.silu(ref)
-    close(out, ref.permute(0, 2, 3, 1), rtol=6e-3, atol=6e-3)
+    for o in (out, out_f, out_f2):
+        close(o, ref.permute(0, 2, 3, 1), rtol=6e-3, atol=6e-3)
 
 
 @pytest.mark.parametrize("C", [192, 320, 768, 1280, 1536])
