@@ -735,8 +735,11 @@ __global__ void patchify_kernel(const T* __restrict__ x, int B, int C, int H, in
 static inline bool gn_fused_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("PFD_GN_TWO_PASS");
-    v = (e && e[0] == '1') ? 0 : 1;
+    // measured (r1 bench10 vs bench9): the activations are L2-resident between the two passes, so the
+    // cooperative single-pass kernel's per-image barrier costs more than the second read saves
+    // (1.31 vs 1.18 ms per UNet evaluation) -> opt-in only.
+    const char* e = getenv("PFD_GN_FUSED");
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }

@@ -29,6 +29,10 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STAGE_A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int SMEM_BUDGET = 232448;         // 227 KiB opt-in limit per CTA
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_STG_BYTES = 1024;         // per epilogue warp: 16 rows x 64 B transpose buffer
+// alignment slack + barriers + epilogue transpose buffers + fp32 bias of the tile (double-buffered)
+constexpr int smem_fixed(int bn) { return 1024 + 256 + EPI_WARPS * EPI_STG_BYTES + 2 * bn * 4; }
 
 struct alignas(64) GemmParams {
   CUtensorMap tmA[PFD_MAX_SEG];
@@ -43,6 +47,7 @@ struct alignas(64) GemmParams {
   int W, H, NB, N;
   int b_batched;
   int num_kb;
+  int b_resident;    // 1: this CTA's B tile (all K) stays in shared memory for all of its tiles
   int splits;        // split-K factor (1 = off); work items = tiles * splits
   int kb_per_split;
   float* ws;         // fp32 partials [splits][m_tiles*128][N] when splits > 1
@@ -62,9 +67,9 @@ template <int BN>
 struct GemmCfg {
   static constexpr int STAGE_B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-  static constexpr int RAW_STAGES = (SMEM_BUDGET - 1024 - 256) / STAGE_BYTES;
+  static constexpr int RAW_STAGES = (SMEM_BUDGET - smem_fixed(BN)) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + smem_fixed(BN);
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128u : (2 * BN <= 256 ? 256u : 512u);
   static_assert(STAGE_B_BYTES % 1024 == 0, "B stage must keep 1024-B swizzle alignment");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
@@ -82,6 +87,20 @@ __device__ __forceinline__ float fast_erf(float x) {
   poly *= t;
   const float y = 1.f - poly * __expf(-ax * ax);
   return copysignf(y, x);
+}
+
+// GELU as x * sigmoid(x * (a + b x^2 + c x^4)), coefficients fitted to the exact erf form on [-8, 8]
+// (max |error| 2.5e-5, tools/fit_gelu.py; fp16 resolution near 1 is 4.9e-4).  The polynomial is evaluated on
+// clamp(x, +-10) because c < 0 would flip its sign beyond |x| = 11.1; at |x| = 10 the sigmoid is already 0 / 1
+// to 3e-9.  9 FMA-pipe instructions + 2 MUFU per element against ~17 + 2 for the A&S erf form.
+__device__ __forceinline__ float gelu_sig(float x) {
+  const float xc = fminf(fmaxf(x, -10.f), 10.f);
+  const float x2 = xc * xc;
+  // coefficients pre-multiplied by -log2(e)
+  const float pl = fmaf(x2, fmaf(x2, 1.01426305e-3f, -1.06775723e-1f), -2.30112135f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * pl));
+  return __fdividef(x, 1.f + e);
 }
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -112,7 +131,37 @@ __device__ __forceinline__ void load8h(const __half* p, float (&f)[8]) {
   }
 }
 
-template <int BN>
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 hadd2x4(const uint4& a, const uint4& b) {
+  uint4 o;
+  const __half2* ah = reinterpret_cast<const __half2*>(&a);
+  const __half2* bh = reinterpret_cast<const __half2*>(&b);
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) oh[i] = __hadd2(ah[i], bh[i]);
+  return o;
+}
+
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// LEAN = true: epilogue for 16-byte-vectorisable outputs (channel-last rows, optional head split) without split-K;
+// LEAN = false keeps the general path (element-strided outputs such as V^T, split-K partials).
+template <int BN, bool LEAN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -122,14 +171,20 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
+  // B-resident mode (small-K GEMMs, which are L2->SM traffic bound): the whole [BN x K] weight tile of this
+  // CTA's fixed n_tile is loaded once; the ring then stages A only (up to STAGES stages of 16 KB).
+  const int nkb_res = p.b_resident ? p.num_kb : 0;
   const uint32_t smemA = base;
-  const uint32_t smemB = base + STAGES * STAGE_A_BYTES;
+  const uint32_t smemB = base + STAGES * STAGE_A_BYTES;               // streaming mode: [STAGES][B tile]
+  const int nst = nkb_res > 0 ? 4 : STAGES;                           // A-ring depth
+  const uint32_t smemBres = base + 4 * STAGE_A_BYTES;                 // resident mode: [num_kb][B tile] after 4 A stages
   const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;
   // barrier layout: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t bres_bar = bars + 8u * (2 * STAGES + 5);
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_g =
       reinterpret_cast<volatile uint32_t*>(gbase + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
@@ -150,6 +205,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 256);
     }
+    mbar_init(bres_bar, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -172,6 +228,13 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (nkb_res > 0 && (int)blockIdx.x < total_work) {
+        // gridDim.x is a multiple of n_tiles -> every tile of this CTA has n_tile == blockIdx.x % n_tiles
+        const int n_tile_fixed = blockIdx.x % p.n_tiles;
+        mbar_expect_tx(bres_bar, (uint32_t)nkb_res * Cfg::STAGE_B_BYTES);
+        for (int kb = 0; kb < nkb_res; ++kb)
+          tma_load_3d(smemBres + kb * Cfg::STAGE_B_BYTES, &p.tmB, bres_bar, kb * BK, n_tile_fixed * BN, 0);
+      }
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         const int tile = work % total_tiles;
         const int split = work / total_tiles;
@@ -196,12 +259,13 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < p.chunks[s]; ++j, ++kbi) {
               if (kbi < kb_begin || kbi >= kb_end) continue;
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+              mbar_expect_tx(full_bar(stage), nkb_res > 0 ? STAGE_A_BYTES : Cfg::STAGE_BYTES);
               tma_load_4d(smemA + stage * STAGE_A_BYTES, &p.tmA[s], full_bar(stage), j * BK,
                           x0 + dx, y0 + dy, n0);
-              tma_load_3d(smemB + stage * Cfg::STAGE_B_BYTES, &p.tmB, full_bar(stage),
-                          kofs + j * BK, n_tile * BN, bcoord);
-              if (++stage == STAGES) {
+              if (nkb_res == 0)
+                tma_load_3d(smemB + stage * Cfg::STAGE_B_BYTES, &p.tmB, full_bar(stage),
+                            kofs + j * BK, n_tile * BN, bcoord);
+              if (++stage == nst) {
                 stage = 0;
                 phase ^= 1u;
               }
@@ -218,6 +282,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (nkb_res > 0 && (int)blockIdx.x < total_work) mbar_wait(bres_bar, 0);
       for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
@@ -230,14 +295,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(smemA + stage * STAGE_A_BYTES);
-          const uint64_t bdesc = make_sw128_kmajor_desc(smemB + stage * Cfg::STAGE_B_BYTES);
+          const uint64_t bdesc = make_sw128_kmajor_desc(nkb_res > 0 ? smemBres + kb * Cfg::STAGE_B_BYTES
+                                                                    : smemB + stage * Cfg::STAGE_B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 fp16 = 32 B inside the 128-B swizzle atom: +2 in the (addr>>4) field
             umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == STAGES) {
+          if (++stage == nst) {
             stage = 0;
             phase ^= 1u;
           }
@@ -290,9 +356,253 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         hcol = ecol / p.cdiv;
         ecol = ecol % p.cdiv;
       }
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * CB;
+      if constexpr (LEAN) {
+        // ---------------- lean path (r1 ncu prof_lin: the general epilogue issued ~270 instructions per 16
+        // columns at ~8 cycles each with 2 warps per scheduler, and every row-per-thread ld/st.global request
+        // touched 32 lines -> small-K GEMMs spent 2.7-5.2 us per tile here against 0.8 us of MMA).
+        //  * the tile's bias is converted to fp32 once into shared memory (double-buffered by accumulator
+        //    stage, one named barrier per tile) -> one FFMA per element (acc * alpha + bias);
+        //  * runs of 32 columns: tcgen05.ld 32 columns, pack to fp16, transpose the warp's 32 rows x 64 B
+        //    through a 1 KB XOR-swizzled buffer (two half-warp passes, conflict-free both ways) so that
+        //    global traffic is 8 rows x 64 B per request;
+        //  * the residual is read in the same coalesced mapping, one run ahead (run 0: before the
+        //    accumulator is ready), and added to the fp16-rounded result in fp16 - the reference's
+        //    `x + conv(h)` on fp16 tensors.
+        const uint32_t fixed0 = base + STAGES * Cfg::STAGE_BYTES + 256;
+        const uint32_t stg = fixed0 + (warp - 2) * EPI_STG_BYTES;
+        const uint32_t sbias = fixed0 + EPI_WARPS * EPI_STG_BYTES + as * (BN * 4);
+        const int et = threadIdx.x - 64;
+        if (et < BN) {
+          // GEGLU weights/bias are packed [value | gate] per n tile (pack_geglu): bias index n_tile * BN + j
+          const int c = geglu ? n_tile * BN + et : col_base + et;
+          const float b = (p.bias != nullptr && c < p.N) ? __half2float(__ldg(p.bias + c)) : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + et * 4), "f"(b) : "memory");
+        }
+        const int cbeg = ch_begin * 16, cend = ch_end * 16;        // this warp's columns inside the tile
+        const int n32 = (cend - cbeg) >> 5;
+        const bool tail16 = ((cend - cbeg) & 16) != 0;
+        const long long my_off = valid ? row_off : -1;
+        // 32-column runs: 4 lanes per row, rows hp*16 + it*8 + lane/4; 16-column run: 2 lanes per row, rows it*16 + lane/2
+        const int cc4 = lane & 3, cc2 = lane & 1;
+        long long roff4[4], roff2[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) roff4[j] = __shfl_sync(0xffffffffu, my_off, (j >> 1) * 16 + (j & 1) * 8 + (lane >> 2));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) roff2[j] = __shfl_sync(0xffffffffu, my_off, j * 16 + (lane >> 1));
+        const __half* resp = p.residual;
+        const bool has_res = resp != nullptr;
+        const float alpha = p.alpha;
+        const int act = p.act;
+        const int n_lim = n_out;
+        // element offset of output column c: head split (c / cdiv) * so_c1 + c % cdiv, or just c
+        auto coff_of = [&](int c) -> long long {
+          return plain_cols ? (long long)c : (long long)(c / p.cdiv) * p.so_c1 + (long long)(c % p.cdiv);
+        };
+        auto load_res32 = [&](int c0, uint4(&dst)[4]) {
+          const int c = col_base + c0 + cc4 * 8;
+          if (has_res && c < n_lim) {
+            const long long co = coff_of(c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (roff4[j] >= 0) dst[j] = __ldg(reinterpret_cast<const uint4*>(resp + roff4[j] + co));
+          }
+        };
+        auto load_res16 = [&](int c0, uint4(&dst)[4]) {
+          const int c = col_base + c0 + cc2 * 8;
+          if (has_res && c < n_lim) {
+            const long long co = coff_of(c);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              if (roff2[j] >= 0) dst[j] = __ldg(reinterpret_cast<const uint4*>(resp + roff2[j] + co));
+          }
+        };
+        if (geglu) {
+          // ------ GEGLU: out[:, col] = value * gelu(gate), runs of 16 output columns (value + gate accumulators)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mbar_wait(tfull_bar(as), aph);
+          tc_fence_after();
+          const uint32_t wr16 = stg + lane * 32;
+          const uint32_t swz16 = (lane >> 2) & 1;
+          for (int ch = ch_begin; ch < ch_end; ++ch) {
+            const int c0 = ch * 16;
+            uint32_t r[16], g[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld16(taddr + CB / 2 + c0, g);
+            tmem_ld_wait();
+            uint32_t h[8];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 b = ld_shared_f4(sbias + (c0 + q4 * 4) * 4);
+              const float4 bg = ld_shared_f4(sbias + (CB / 2 + c0 + q4 * 4) * 4);
+              // reference: x, gate = proj(x).chunk(2) are fp16 tensors; x * gelu(gate) in fp16 (attention.py:50-51)
+              const __half2 a01 = __floats2half2_rn(fmaf(__uint_as_float(r[q4 * 4]), alpha, b.x), fmaf(__uint_as_float(r[q4 * 4 + 1]), alpha, b.y));
+              const __half2 a23 = __floats2half2_rn(fmaf(__uint_as_float(r[q4 * 4 + 2]), alpha, b.z), fmaf(__uint_as_float(r[q4 * 4 + 3]), alpha, b.w));
+              const float2 g01 = __half22float2(__floats2half2_rn(fmaf(__uint_as_float(g[q4 * 4]), alpha, bg.x), fmaf(__uint_as_float(g[q4 * 4 + 1]), alpha, bg.y)));
+              const float2 g23 = __half22float2(__floats2half2_rn(fmaf(__uint_as_float(g[q4 * 4 + 2]), alpha, bg.z), fmaf(__uint_as_float(g[q4 * 4 + 3]), alpha, bg.w)));
+              const __half2 o01 = __hmul2(a01, __floats2half2_rn(gelu_sig(g01.x), gelu_sig(g01.y)));
+              const __half2 o23 = __hmul2(a23, __floats2half2_rn(gelu_sig(g23.x), gelu_sig(g23.y)));
+              h[q4 * 2] = *reinterpret_cast<const uint32_t*>(&o01);
+              h[q4 * 2 + 1] = *reinterpret_cast<const uint32_t*>(&o23);
+            }
+            st_shared_v4(wr16 + ((0 ^ swz16) << 4), h[0], h[1], h[2], h[3]);
+            st_shared_v4(wr16 + ((1 ^ swz16) << 4), h[4], h[5], h[6], h[7]);
+            __syncwarp();
+            const int c = col_base + c0 + cc2 * 8;
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int rr = it * 16 + (lane >> 1);
+              if (roff2[it] >= 0) {
+                const uint4 o = ld_shared_v4(stg + rr * 32 + ((cc2 ^ ((rr >> 2) & 1)) << 4));
+                *reinterpret_cast<uint4*>(p.out + roff2[it] + c) = o;
+              }
+            }
+            __syncwarp();
+          }
+          tc_fence_before();
+          mbar_arrive(tempty_bar(as));
+          continue;
+        }
+        uint4 ra[4], rb[4];
+        int c0 = cbeg;
+        if (n32 > 0) load_res32(c0, ra);
+        else if (tail16) load_res16(c0, ra);
+        asm volatile("bar.sync 1, 256;" ::: "memory");            // bias of this tile visible to all epilogue warps
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after();
+        const uint32_t wr32 = stg + (lane & 15) * 64;
+        const uint32_t swz32 = ((lane & 15) >> 1) & 3;
+        const uint32_t rd32 = stg + (lane >> 2) * 64 + ((cc4 ^ ((lane >> 3) & 3)) << 4);
+        for (int i = 0; i < n32; ++i, c0 += 32) {
+          if (col_base + c0 >= n_lim) break;                       // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          if (i + 1 < n32) load_res32(c0 + 32, rb);
+          else if (tail16) load_res16(c0 + 32, rb);
+          tmem_ld_wait();
+          uint32_t h[16];
+          if (rowadd_row == nullptr && act == PFD_ACT_NONE) {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 b = ld_shared_f4(sbias + (c0 + q4 * 4) * 4);
+              h[q4 * 2] = pack_h2(fmaf(__uint_as_float(r[q4 * 4]), alpha, b.x), fmaf(__uint_as_float(r[q4 * 4 + 1]), alpha, b.y));
+              h[q4 * 2 + 1] = pack_h2(fmaf(__uint_as_float(r[q4 * 4 + 2]), alpha, b.z), fmaf(__uint_as_float(r[q4 * 4 + 3]), alpha, b.w));
+            }
+          } else {
+            // per-image row add (time embedding) and/or activation: same order as the reference
+            // (conv + bias) + emb -> act
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+              float v[8];
+              const float4 b0 = ld_shared_f4(sbias + (c0 + q8 * 8) * 4);
+              const float4 b1 = ld_shared_f4(sbias + (c0 + q8 * 8 + 4) * 4);
+              v[0] = fmaf(__uint_as_float(r[q8 * 8]), alpha, b0.x);
+              v[1] = fmaf(__uint_as_float(r[q8 * 8 + 1]), alpha, b0.y);
+              v[2] = fmaf(__uint_as_float(r[q8 * 8 + 2]), alpha, b0.z);
+              v[3] = fmaf(__uint_as_float(r[q8 * 8 + 3]), alpha, b0.w);
+              v[4] = fmaf(__uint_as_float(r[q8 * 8 + 4]), alpha, b1.x);
+              v[5] = fmaf(__uint_as_float(r[q8 * 8 + 5]), alpha, b1.y);
+              v[6] = fmaf(__uint_as_float(r[q8 * 8 + 6]), alpha, b1.z);
+              v[7] = fmaf(__uint_as_float(r[q8 * 8 + 7]), alpha, b1.w);
+              if (rowadd_row != nullptr && valid && col_base + c0 + q8 * 8 < n_lim) {
+                float rv[8];
+                load8h(rowadd_row + col_base + c0 + q8 * 8, rv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += rv[i];
+              }
+              if (act != PFD_ACT_NONE) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], act);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h[q8 * 4 + i] = pack_h2(v[2 * i], v[2 * i + 1]);
+            }
+          }
+          const int c = col_base + c0 + cc4 * 8;
+          const bool colok = c < n_lim;
+          const long long co = coff_of(c);
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {
+            if ((lane >> 4) == hp) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                st_shared_v4(wr32 + ((k ^ swz32) << 4), h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int j = hp * 2 + it;
+              if (colok && roff4[j] >= 0) {
+                uint4 o = ld_shared_v4(rd32 + it * 512);
+                if (has_res) o = hadd2x4(o, ra[j]);
+                *reinterpret_cast<uint4*>(p.out + roff4[j] + co) = o;
+              }
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ra[j] = rb[j];
+        }
+        if (tail16 && col_base + c0 < n_lim) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          uint32_t h[8];
+#pragma unroll
+          for (int q8 = 0; q8 < 2; ++q8) {
+            float v[8];
+            const float4 b0 = ld_shared_f4(sbias + (c0 + q8 * 8) * 4);
+            const float4 b1 = ld_shared_f4(sbias + (c0 + q8 * 8 + 4) * 4);
+            v[0] = fmaf(__uint_as_float(r[q8 * 8]), alpha, b0.x);
+            v[1] = fmaf(__uint_as_float(r[q8 * 8 + 1]), alpha, b0.y);
+            v[2] = fmaf(__uint_as_float(r[q8 * 8 + 2]), alpha, b0.z);
+            v[3] = fmaf(__uint_as_float(r[q8 * 8 + 3]), alpha, b0.w);
+            v[4] = fmaf(__uint_as_float(r[q8 * 8 + 4]), alpha, b1.x);
+            v[5] = fmaf(__uint_as_float(r[q8 * 8 + 5]), alpha, b1.y);
+            v[6] = fmaf(__uint_as_float(r[q8 * 8 + 6]), alpha, b1.z);
+            v[7] = fmaf(__uint_as_float(r[q8 * 8 + 7]), alpha, b1.w);
+            if (rowadd_row != nullptr && valid && col_base + c0 + q8 * 8 < n_lim) {
+              float rv[8];
+              load8h(rowadd_row + col_base + c0 + q8 * 8, rv);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += rv[i];
+            }
+            if (act != PFD_ACT_NONE) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = act_apply(v[i], act);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[q8 * 4 + i] = pack_h2(v[2 * i], v[2 * i + 1]);
+          }
+          // 32 rows x 32 B in one pass: chunk k of row l at l*32 + ((k ^ ((l >> 2) & 1)) << 4)
+          const uint32_t wr16 = stg + lane * 32;
+          const uint32_t swz16 = (lane >> 2) & 1;
+          st_shared_v4(wr16 + ((0 ^ swz16) << 4), h[0], h[1], h[2], h[3]);
+          st_shared_v4(wr16 + ((1 ^ swz16) << 4), h[4], h[5], h[6], h[7]);
+          __syncwarp();
+          const int c = col_base + c0 + cc2 * 8;
+          if (c < n_lim) {
+            const long long co = coff_of(c);
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int rr = it * 16 + (lane >> 1);
+              if (roff2[it] >= 0) {
+                uint4 o = ld_shared_v4(stg + rr * 32 + ((cc2 ^ ((rr >> 2) & 1)) << 4));
+                if (has_res) o = hadd2x4(o, ra[it]);
+                *reinterpret_cast<uint4*>(p.out + roff2[it] + co) = o;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
+      if (!LEAN) {
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after();
+      }
       if (p.splits > 1) {
         // split-K: raw fp32 partials -> workspace; bias/activation/residual happen in splitk_finish_kernel
         float* wrow = p.ws + ((long long)split * m_tiles * BM + (long long)m_tile * BM + row) * p.N;
@@ -605,6 +915,15 @@ splitk_finish_kernel(const __grid_constant__ GemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------ host
+static inline bool gemm_bres_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PFD_BRES");      // opt-in: measured neutral-to-slower (r1 linperf / ksweep2 logs)
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 constexpr size_t SPLITK_WS_BYTES = 64ull << 20;
 static float* splitk_workspace(cudaStream_t st) {
   // one workspace per stream (calls on distinct streams may run concurrently); allocated on first use,
@@ -667,18 +986,43 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
 
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
-template <int BN>
-static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+template <int BN, bool LEAN>
+static int launch_gemm_t(const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_done = true;
   }
-  launch_k(gemm_tc_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
+  launch_k(gemm_tc_kernel<BN, LEAN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
   return check_launch("pfd_gemm_f16");
+}
+
+static inline bool gemm_lean_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PFD_NO_LEAN_EPI");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BN>
+static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+  const bool lean = gemm_lean_enabled() && p.vec_ok && p.splits == 1;
+  static int trace = -1;
+  if (trace < 0) {
+    const char* e = getenv("PFD_GEMM_TRACE");
+    trace = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (trace)   // one line per launch, joined with an ncu launch list by tools/gemm_breakdown.py
+    fprintf(stderr, "GEMMTRACE M=%lld N=%d K=%d nseg=%d taps=%d stride=%d act=%d bias=%d res=%d rowadd=%d BN=%d lean=%d "
+            "splits=%d grid=%d batched=%d vec=%d plain=%d\n", (long long)p.W * p.H * p.NB, p.N, p.num_kb * BK, p.nseg,
+            p.taps[0], p.stride, p.act, p.bias != nullptr, p.residual != nullptr, p.rowadd != nullptr, BN, (int)lean,
+            p.splits, grid, p.b_batched, p.vec_ok, (int)(p.cdiv >= p.N));
+  return lean ? launch_gemm_t<BN, true>(p, grid, stream) : launch_gemm_t<BN, false>(p, grid, stream);
 }
 
 }  // namespace pfd
@@ -819,6 +1163,29 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
       }
     }
   }
+  // ---- B-resident mode (small-K GEMMs are L2->SM traffic bound): plain (1 segment, 1 tap, shared weights, no
+  //      split) GEMMs whose [BN x K] weight tile fits beside a 4-stage A ring keep it in shared memory for all
+  //      tiles of the CTA; requires n_tile fixed per CTA (grid = multiple of n_tiles).
+  p.b_resident = 0;
+  if (d->nseg == 1 && d->taps[0] == 1 && !p.b_batched && p.splits == 1 && gemm_bres_enabled()) {
+    const int try_bn[3] = {BNsel, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      const int bn_c = try_bn[i];
+      if (d->bn_force && bn_c != d->bn_force) continue;
+      if (geglu && (d->N % bn_c)) continue;
+      const long long nt = cdivll(d->N, bn_c);
+      if (nt > sms || m_tiles * nt < 2LL * sms) continue;
+      const size_t tile_b = (size_t)bn_c * BK * 2;
+      const size_t raw = (size_t)(SMEM_BUDGET - smem_fixed(bn_c)) / (STAGE_A_BYTES + tile_b);
+      const size_t total_smem = (raw > 8 ? 8 : raw) * (STAGE_A_BYTES + tile_b);
+      if ((size_t)num_kb * tile_b + 4u * STAGE_A_BYTES <= total_smem) {
+        p.b_resident = 1;
+        BNsel = bn_c;
+        p.n_tiles = (int)nt;
+        break;
+      }
+    }
+  }
   {
     const long long nbatch = p.b_batched ? d->NB : 1;
     cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)nbatch};
@@ -830,7 +1197,8 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   }
 
   const long long total = m_tiles * p.n_tiles * p.splits;
-  const int grid = (int)(total < sms ? total : sms);
+  int grid = (int)(total < sms ? total : sms);
+  if (p.b_resident) grid = (sms / p.n_tiles) * p.n_tiles;   // n_tile fixed per CTA
   int rc;
   switch (BNsel) {
     case 64: rc = launch_gemm<64>(p, grid, st); break;

@@ -143,7 +143,7 @@ def test_groupnorm(nv, C1, C2, HW, silu):
     gamma, beta = rnd(C, seed=4) + 1.0, rnd(C, seed=5)
     out = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)          # scratch ring exhausted -> two-pass kernels
     nv.gn_reset()
-    out_f = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)        # pre-zeroed slot -> single-pass kernel
+    out_f = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)        # pre-zeroed ring slot (no memset launch)
     out_f2 = nv.groupnorm(x1, gamma, beta, 1e-5, silu=silu, x2=x2)       # next slot
     torch.cuda.synchronize()
     xc = x1 if x2 is None else torch.cat([x1, x2], 3)
@@ -152,6 +152,29 @@ def test_groupnorm(nv, C1, C2, HW, silu):
         ref = F.silu(ref)
     for o in (out, out_f, out_f2):
         close(o, ref.permute(0, 2, 3, 1), rtol=6e-3, atol=6e-3)
+
+
+def test_groupnorm_single_pass_opt_in():
+    """PFD_GN_FUSED=1 selects the cooperative single-pass GroupNorm (opt-in: measured slower than the two-pass
+    kernels on L2-resident activations).  The switch is read once per process -> run in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, torch.nn.functional as F\n"
+        "from pfd_b200 import native as nv\n"
+        "torch.manual_seed(0)\n"
+        "x = (torch.randn(2, 32, 32, 320, device='cuda') * 2 + 0.5).half()\n"
+        "g = (torch.randn(320, device='cuda') + 1).half(); b = torch.randn(320, device='cuda').half()\n"
+        "nv.gn_reset()\n"
+        "o = nv.groupnorm(x, g, b, 1e-5, silu=True)\n"
+        "r = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, g.float(), b.float(), 1e-5)).permute(0, 2, 3, 1)\n"
+        "torch.testing.assert_close(o.float(), r, rtol=6e-3, atol=6e-3)\n"
+        "print('ok')\n")
+    env = dict(os.environ, PFD_GN_FUSED="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("C", [192, 320, 768, 1280, 1536])
