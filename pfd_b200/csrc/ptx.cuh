@@ -27,14 +27,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Suspend-time hint: with the default (system-dependent, short) limit a waiting thread re-polls every few tens
+// of ns, and ncu showed ~27 % of the flash kernel's issued instructions were polling (SYNCS/BRA/YIELD/IADD3/
+// ISETP) competing with the softmax warps for issue slots.  The thread still resumes as soon as the phase
+// completes; the hint only bounds how long the hardware may keep it parked.
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = 4096;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -42,7 +47,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
+    if (++spins > (1u << 22)) {
       asm volatile("trap;");
     }
   }
