@@ -31,6 +31,11 @@ constexpr int FA_BQ = 128;
 constexpr int FA_BKV = 64;
 constexpr int FA_THREADS = 192;
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
   uint32_t y;
   asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
@@ -215,10 +220,12 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
     const int row = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
-    const float sc = p.scale;
-    const __half2 log2e2 = __float2half2_rn(LOG2E);
-    const __half2 ninf2 = __float2half2_rn(-INFINITY);
-    float m = -INFINITY;
+    const float c2 = p.scale * LOG2E;                   // logits in log2 units: t = s * c2
+    // Running reference exponent (log2 units).  It only moves when the block maximum exceeds it by more than
+    // RESCALE_TAU (lazy rescaling: P <= 2^TAU stays far inside fp16 range and the fp32 accumulators absorb the
+    // common factor, which cancels in O / l), so the TMEM read-modify-write of O is rare after the first blocks.
+    constexpr float RESCALE_TAU = 8.f;
+    float mref = -INFINITY;
     uint8_t* prow0 = gP + row * 128;
     const int rsw = row & 7;
     for (int j = 0; j < nblk; ++j) {
@@ -228,61 +235,55 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       mbar_wait(bar_s_full(sb), us & 1);
       tc_fence_after();
       const uint32_t tS = tmem_base + lane_off + sb * FA_BKV;
-      // single pass over S (TMEM reads are the scarce resource: 64 B/clk/SM): logits -> packed fp16 in
-      // registers (32 x half2 for 64 keys), running max with HMNMX2
-      __half2 v[FA_BKV / 2];
-      __half2 mx2 = ninf2;
-      {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tS, r0);
-        tmem_ld32(tS + 32, r1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          v[i >> 1] = __floats2half2_rn(__uint_as_float(r0[i]) * sc, __uint_as_float(r0[i + 1]) * sc);
-          v[16 + (i >> 1)] = __floats2half2_rn(__uint_as_float(r1[i]) * sc, __uint_as_float(r1[i + 1]) * sc);
-        }
-      }
+      // single pass over S (fp32 logits of this thread's query row against 64 keys)
+      uint32_t r[FA_BKV];
+      tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_s_free(sb));                      // S buffer may now be overwritten by the next QK^T
       if (partial) {
 #pragma unroll
-        for (int i = 0; i < FA_BKV / 2; ++i) {
-          if (2 * i >= kvalid) v[i] = ninf2;
-          else if (2 * i + 1 >= kvalid) v[i] = __halves2half2(__low2half(v[i]), __float2half_rn(-INFINITY));
-        }
+        for (int i = 0; i < FA_BKV; ++i)
+          if (i >= kvalid) r[i] = 0xff800000u;          // -inf: masked keys contribute exp2(-inf) = 0
       }
+      // block maximum: four independent 3-input max chains
+      float mx[4];
 #pragma unroll
-      for (int i = 0; i < FA_BKV / 2; ++i) mx2 = __hmax2(mx2, v[i]);
-      const float m_new = fmaxf(m, fmaxf(__low2float(mx2), __high2float(mx2)));
-      const float alpha = (j == 0) ? 0.f : fast_exp2((m - m_new) * LOG2E);
-      const __half2 mh2 = __float2half2_rn(m_new);     // exact: m_new is an fp16 value
-      if (Cfg::NPB == 1 && j > 0) {
-        mbar_wait(bar_pv_done, (j - 1) & 1);           // single P buffer: PV_{j-1} must have consumed it
-        tc_fence_after();
+      for (int q = 0; q < 4; ++q) {
+        mx[q] = fmax3(__uint_as_float(r[q * 16]), __uint_as_float(r[q * 16 + 1]), __uint_as_float(r[q * 16 + 2]));
+#pragma unroll
+        for (int i = 3; i + 1 < 16; i += 2)
+          mx[q] = fmax3(mx[q], __uint_as_float(r[q * 16 + i]), __uint_as_float(r[q * 16 + i + 1]));
+        mx[q] = fmaxf(mx[q], __uint_as_float(r[q * 16 + 15]));
       }
-      uint8_t* prow = prow0 + (Cfg::NPB == 2 ? (j & 1) * Cfg::P_BYTES : 0);
-      // p = 2^((v - m) * log2e) on packed halves -> P tile in shared memory (swizzled K-major A operand)
+      const float mb = fmax3(fmaxf(mx[0], mx[1]), mx[2], mx[3]) * c2;
+      const bool move = mb > mref + RESCALE_TAU;        // always true for j == 0 (mref = -inf)
+      const float mnew = move ? mb : mref;
+      const float alpha = move ? fast_exp2(mref - mnew) : 1.f;   // j == 0: exp2(-inf) = 0, unused
+      mref = mnew;
+      const float nm = -mnew;
+      // p = 2^(s * c2 - mref) -> packed fp16 (registers), overlapping PV_{j-1}
+      uint32_t pk[FA_BKV / 2];
 #pragma unroll
-      for (int g = 0; g < FA_BKV / 8; ++g) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const __half2 t = __hmul2(__hsub2(v[g * 4 + i], mh2), log2e2);
-          pk[i] = ex2_f16x2(*reinterpret_cast<const uint32_t*>(&t));
-        }
-        *reinterpret_cast<uint4*>(prow + ((g ^ rsw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int i = 0; i < FA_BKV / 2; ++i) {
+        const float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), c2, nm));
+        const float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), c2, nm));
+        const __half2 h = __floats2half2_rn(e0, e1);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
       }
-      m = m_new;
-      if (Cfg::NPB == 2 && j > 0) {
-        // double-buffered P: exp/write of this block overlapped PV_{j-1}; O must be stable before the
-        // rescale below and before PV_j accumulates into it (also frees P[(j+1)&1] for the next block)
+      if (j > 0) {
+        // single P buffer / running O: PV_{j-1} must have consumed P and finished accumulating
         mbar_wait(bar_pv_done, (j - 1) & 1);
         tc_fence_after();
       }
-      // rescale the running output (and its row-sum column) when this warp's maxima moved
+      uint8_t* prow = prow0 + (Cfg::NPB == 2 ? (j & 1) * Cfg::P_BYTES : 0);
+#pragma unroll
+      for (int g = 0; g < FA_BKV / 8; ++g)
+        *reinterpret_cast<uint4*>(prow + ((g ^ rsw) << 4)) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      // rescale the running output (and its row-sum column) when a reference exponent of this warp moved
       if (j > 0) {
-        const bool need = __any_sync(0xffffffffu, alpha != 1.f);
+        const bool need = __any_sync(0xffffffffu, move);
         if (need) {
           for (int c = 0; c < dN / 16; ++c) {
             uint32_t o[16];
