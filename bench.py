@@ -340,6 +340,30 @@ def run_ours(args):
     e2e = world * B * args.steps / (ms_e2e / 1000.0)
     finite = bool(torch.isfinite(im.float()).all().item())
 
+    # ---- informational: device time of the three stages of one request (outside the timed regions)
+    stage_ms = None
+    if rank == 0:
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                r = fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps, r
+        t_ctx, c1 = timed(lambda: net.ctx_encode(img_dev, "image"))
+        cB = c1.repeat(B, 1, 1)
+        uB = torch.zeros_like(cB)
+        t_smp, (xs, _) = timed(lambda: sampler.sample(
+            steps=args.ddim_steps, x_info={"type": "image"},
+            c_info={"type": "image", "conditioning": cB, "unconditional_conditioning": uB,
+                    "unconditional_guidance_scale": 2.0, "control": None},
+            shape=[B, 4, L, L], verbose=False, eta=0.0), reps=2)
+        t_vae, _ = timed(lambda: net.vae_decode(xs, "image"))
+        stage_ms = {"seecoder_encode": t_ctx, "ddim_sampling": t_smp, "vae_decode": t_vae}
+
     if rank == 0:
         peak_t = peaks.get("bf16_tflops_sustained", 1400.0)
         which = "of measured (sustained, MEASURED_PEAKS.json)" if peaks else "of fallback"
@@ -370,7 +394,7 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": img_host.numel() * 2,
                         "d2h_bytes_per_step": out_host.numel() * 2},
-                "gpu_launches": int(launches), "clocks": clk, "output_finite": finite}
+                "gpu_launches": int(launches), "clocks": clk, "output_finite": finite, "stage_ms": stage_ms}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -31,6 +31,18 @@ constexpr int FA_BQ = 128;
 constexpr int FA_BKV = 64;
 constexpr int FA_THREADS = 192;
 
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel. error 7.5e-5 - the fp16 P
+// operand resolves 4.9e-4): used for a fraction of the elements so that the MUFU pipe (58 % busy in the ncu
+// capture of the level-0 self-attention, the busiest pipe) is not the only producer of exponentials.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -30.f);                                    // 2^-30 rounds to 0 in fp16
+  const float xf = x + 12582912.f;                        // 1.5 * 2^23: round(x) sits in the low mantissa bits
+  const float f = x - (xf - 12582912.f);                  // [-0.5, 0.5]
+  float pl = fmaf(f, 0.05516102f, 0.24261291f);
+  pl = fmaf(pl, f, 0.69326254f);
+  pl = fmaf(pl, f, 0.99992796f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(xf) << 23));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -51,6 +63,7 @@ struct alignas(64) FlashParams {
   CUtensorMap tmQ, tmK, tmV;
   int Nq, Nk, heads, d;
   int nblk;
+  int poly_exp;                // 1: every 4th exponential on the FMA pipe (PFD_FLASH_POLY=1)
   float scale;
   __half* out;
   long long o_sb, o_sq, o_sh;  // element strides: batch, query row, head
@@ -265,12 +278,24 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       const float nm = -mnew;
       // p = 2^(s * c2 - mref) -> packed fp16 (registers), overlapping PV_{j-1}
       uint32_t pk[FA_BKV / 2];
+      if (p.poly_exp) {
 #pragma unroll
-      for (int i = 0; i < FA_BKV / 2; ++i) {
-        const float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), c2, nm));
-        const float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), c2, nm));
-        const __half2 h = __floats2half2_rn(e0, e1);
-        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int i = 0; i < FA_BKV / 2; ++i) {
+          const float t0 = fmaf(__uint_as_float(r[2 * i]), c2, nm);
+          const float t1 = fmaf(__uint_as_float(r[2 * i + 1]), c2, nm);
+          const float e0 = fast_exp2(t0);
+          const float e1 = (i & 1) ? poly_exp2(t1) : fast_exp2(t1);   // every 4th element on the FMA pipe
+          const __half2 h = __floats2half2_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < FA_BKV / 2; ++i) {
+          const float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), c2, nm));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), c2, nm));
+          const __half2 h = __floats2half2_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
       }
       if (j > 0) {
         // single P buffer / running O: PV_{j-1} must have consumed P and finished accumulating
@@ -405,6 +430,14 @@ extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, 
   if (int rc = encode4d(&p.tmK, k, d, Nk, heads, B, k_strides[2], k_strides[1], k_strides[0], FA_BKV, "K")) return rc;
   if (int rc = encode4d(&p.tmV, vt, Nk, d, heads, B, vt_strides[2], vt_strides[1], vt_strides[0], (cuuint32_t)d, "V^T")) return rc;
   p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.d = d;
+  {
+    static int poly = -1;
+    if (poly < 0) {
+      const char* e = getenv("PFD_FLASH_POLY");
+      poly = (e && e[0] == '1') ? 1 : 0;
+    }
+    p.poly_exp = poly;
+  }
   p.nblk = (Nk + FA_BKV - 1) / FA_BKV;
   p.scale = scale;
   p.out = static_cast<__half*>(out);

@@ -732,6 +732,172 @@ __global__ void patchify_kernel(const T* __restrict__ x, int B, int C, int H, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-pass GroupNorm(+SiLU) on a thread-block cluster.  One cluster of GNC_CS CTAs owns (image n, G consecutive
+// groups): CTA r keeps pixels [r*npc, (r+1)*npc) x (G*cpg channels) in shared memory, the group statistics are
+// reduced across the cluster through distributed shared memory (mean first, then the centred second moment from
+// the cached slice: numerically the textbook two-pass form in fp32), and the slice is normalised straight out of
+// shared memory.  One HBM read + one write and ONE launch per GroupNorm (the stats + apply pair cost two ~5 us
+// launch floors and a second read; the grid-wide spin barrier of gn_fused_kernel cost more than it saved).
+constexpr int GNC_CS = 8;         // portable maximum cluster size
+constexpr int GNC_THREADS = 512;
+
+__device__ __forceinline__ void cluster_arrive_rel() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acq() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(GNC_THREADS, 1)
+gn_cluster_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int HW, int groups,
+                  int G, int npc, const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
+                  int silu, __half* __restrict__ out, float inv_cnt) {
+  extern __shared__ uint4 gnc_smem[];
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int Cs = G * cpg;               // channels of this cluster (multiple of 8)
+  const int ncv = Cs / 8;
+  const int nsub = groups / G;
+  const uint32_t rank = cluster_rank();
+  const int cl = blockIdx.x / GNC_CS;
+  const int n = cl / nsub, gs = cl % nsub;
+  const int c0 = gs * Cs;
+  const int p0 = (int)rank * npc;
+  const int np = max(0, min(HW, p0 + npc) - p0);
+  uint4* slice = gnc_smem;
+  float* s_acc = reinterpret_cast<float*>(slice + (size_t)npc * ncv);   // [G] block accumulators
+  float* s_part1 = s_acc + GN_MAX_GROUPS;                                 // [G] this CTA's sum        (read by peers)
+  float* s_part2 = s_part1 + GN_MAX_GROUPS;                               // [G] this CTA's centred sq (read by peers)
+  float* s_mean = s_part2 + GN_MAX_GROUPS;
+  float* s_rstd = s_mean + GN_MAX_GROUPS;
+  const int tid = threadIdx.x;
+  if (tid < GN_MAX_GROUPS) s_acc[tid] = 0.f;
+  const int lanes = GNC_THREADS / ncv;      // >= 1 (ncv <= 320)
+  const int cv = tid % ncv;
+  const int lp = tid / ncv;
+  const bool active = lp < lanes;
+  const int c = c0 + cv * 8;                // global channel of this thread's vector
+  const int gl0 = (cv * 8) / cpg;           // first local group the vector touches
+  const int split = min(8, (gl0 + 1) * cpg - cv * 8);   // elements [0, split) belong to gl0, the rest to gl0 + 1
+  pdl_enter();
+  __syncthreads();
+  // ---- phase 1: load the slice, per-group sums
+  float a0 = 0.f, a1 = 0.f;
+  if (active) {
+    float sm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[i] = 0.f;
+    for (int pix = lp; pix < np; pix += lanes) {
+      const uint4 u = gn_load(x1, c1, x2, c2, (long long)n * HW + p0 + pix, c);
+      slice[(size_t)pix * ncv + cv] = u;
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm[i] += f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < split) a0 += sm[i];
+      else a1 += sm[i];
+    }
+    atomicAdd(&s_acc[gl0], a0);
+    if (split < 8) atomicAdd(&s_acc[gl0 + 1], a1);
+  }
+  __syncthreads();
+  if (tid < G) {
+    s_part1[tid] = s_acc[tid];
+    s_acc[tid] = 0.f;
+  }
+  cluster_arrive_rel();
+  cluster_wait_acq();
+  if (tid < G) {
+    float t = 0.f;
+    const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part1[tid]));
+#pragma unroll
+    for (int r = 0; r < GNC_CS; ++r) t += ld_dsmem_f32(la, (uint32_t)r);
+    s_mean[tid] = t * inv_cnt;
+  }
+  __syncthreads();
+  // ---- phase 2: centred second moment from the cached slice
+  if (active) {
+    const float m0 = s_mean[gl0];
+    const float m1 = split < 8 ? s_mean[gl0 + 1] : 0.f;
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = 0.f;
+    for (int pix = lp; pix < np; pix += lanes) {
+      float f[8];
+      unpack8(slice[(size_t)pix * ncv + cv], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dlt = f[i] - (i < split ? m0 : m1);
+        q[i] = fmaf(dlt, dlt, q[i]);
+      }
+    }
+    a0 = a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < split) a0 += q[i];
+      else a1 += q[i];
+    }
+    atomicAdd(&s_acc[gl0], a0);
+    if (split < 8) atomicAdd(&s_acc[gl0 + 1], a1);
+  }
+  __syncthreads();
+  if (tid < G) s_part2[tid] = s_acc[tid];
+  cluster_arrive_rel();
+  cluster_wait_acq();
+  if (tid < G) {
+    float t = 0.f;
+    const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part2[tid]));
+#pragma unroll
+    for (int r = 0; r < GNC_CS; ++r) t += ld_dsmem_f32(la, (uint32_t)r);
+    s_rstd[tid] = rsqrtf(t * inv_cnt + eps);
+  }
+  // peers may read this CTA's partials until they pass this point: arrive now, wait right before exit
+  cluster_arrive_rel();
+  __syncthreads();
+  // ---- phase 3: normalise (+SiLU) straight out of shared memory
+  if (active) {
+    float gm[8], bt[8], mu[8], rs[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + c)), gm);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c)), bt);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = i < split ? gl0 : gl0 + 1;
+      rs[i] = s_rstd[g] * gm[i];
+      mu[i] = bt[i] - s_mean[g] * rs[i];          // y = x * rs + mu
+    }
+    for (int pix = lp; pix < np; pix += lanes) {
+      float f[8];
+      unpack8(slice[(size_t)pix * ncv + cv], f);
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float y0 = fmaf(f[2 * i], rs[2 * i], mu[2 * i]);
+        float y1 = fmaf(f[2 * i + 1], rs[2 * i + 1], mu[2 * i + 1]);
+        if (silu) {
+          y0 = __fdividef(y0, 1.f + __expf(-y0));
+          y1 = __fdividef(y1, 1.f + __expf(-y1));
+        }
+        oh[i] = __floats2half2_rn(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(out + ((long long)n * HW + p0 + pix) * C + c) = o;
+    }
+  }
+  cluster_wait_acq();
+}
+
 static inline bool gn_fused_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -766,12 +932,67 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   if (!ws) return set_error("pfd_groupnorm_f16: workspace required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* dws = reinterpret_cast<double*>(ws);
-  if (zero_ws) cudaMemsetAsync(dws, 0, sizeof(double) * 2 * NB * groups, st);
   const int vecs = C / 8;
   // block = largest multiple of vecs that fits 256 threads (or 320 for C = 2560); wide rows fall back to 256
   int threads = vecs <= 320 ? (vecs <= 256 ? (256 / vecs) * vecs : vecs) : 256;
   if (threads < 64) threads = vecs * ((64 + vecs - 1) / vecs);
   const double inv_cnt = 1.0 / ((double)HW * (C / groups));
+  // ---- single-pass cluster path: one 8-CTA cluster per (image, G groups), slice cached in shared memory
+  {
+    static int cl_mode = -1;       // -1 unknown, 0 off, 1 on
+    if (cl_mode < 0) {
+      // opt-in: correct, but measured ~2x slower than the two-pass kernels on every UNet shape (r1 gn_perf.log:
+      // 1.91 vs 1.04 ms per evaluation) - cluster launches of 8 x 512 threads cost more than the second read saves
+      const char* e = getenv("PFD_GN_CLUSTER");
+      cl_mode = (e && e[0] == '1') ? 1 : 0;
+    }
+    const int cpg = C / groups;
+    if (cl_mode == 1 && cpg >= 8 && HW >= GNC_CS && HW <= (1 << 24)) {
+      const int npc = (int)((HW + GNC_CS - 1) / GNC_CS);
+      const size_t slice_max = 200 * 1024;
+      int Gsel = 0;
+      for (int G = groups; G >= 1; --G) {
+        if (groups % G) continue;
+        const int Cs = G * cpg;
+        if (Cs % 8 || Cs / 8 > GNC_THREADS) continue;
+        if ((size_t)npc * (Cs / 8) * 16 > slice_max) continue;
+        Gsel = G;                                                   // valid; keep shrinking until the machine is filled
+        if ((long long)NB * (groups / G) * GNC_CS >= num_sms()) break;
+      }
+      if (Gsel > 0) {
+        const int Cs = Gsel * cpg;
+        const size_t smem = (size_t)npc * (Cs / 8) * 16 + 5 * GN_MAX_GROUPS * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+          cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(slice_max + 5 * GN_MAX_GROUPS * sizeof(float)));
+          attr_set = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((long long)NB * (groups / Gsel) * GNC_CS));
+        cfg.blockDim = dim3(GNC_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = GNC_CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = use_pdl() ? 2 : 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, gn_cluster_kernel, static_cast<const __half*>(x1), (int)c1,
+                                            static_cast<const __half*>(x2), (int)c2, (int)HW, (int)groups, Gsel, npc,
+                                            static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps,
+                                            (int)silu, static_cast<__half*>(out), (float)inv_cnt);
+        if (le == cudaSuccess) return check_launch("gn_cluster");
+        (void)cudaGetLastError();     // cluster launch rejected on this device/config: use the two-pass kernels
+        cl_mode = 0;
+      }
+    }
+  }
+  if (zero_ws) cudaMemsetAsync(dws, 0, sizeof(double) * 2 * NB * groups, st);
   // ---- single-pass path (chunk cached in shared memory, per-image arrival barrier) when the whole grid can be
   //      co-resident; counters live right behind the fp64 sums in the (pre-zeroed) scratch slot
   if (!zero_ws && vecs <= 320 && gn_fused_enabled()) {

@@ -133,7 +133,8 @@ def test_bmm_nt_headsplit(nv):
 
 
 @pytest.mark.parametrize("C1,C2,HW,silu", [(320, 0, 4096, True), (1280, 640, 256, True), (640, 0, 1024, False),
-                                           (128, 0, 65536, True), (64, 64, 64, True)])
+                                           (128, 0, 65536, True), (64, 64, 64, True), (640, 320, 100, True),
+                                           (1280, 1280, 64, True), (320, 0, 9, False)])
 def test_groupnorm(nv, C1, C2, HW, silu):
     NB = 2
     side = int(math.isqrt(HW))
@@ -155,8 +156,10 @@ def test_groupnorm(nv, C1, C2, HW, silu):
 
 
 def test_groupnorm_single_pass_opt_in():
-    """PFD_GN_FUSED=1 selects the cooperative single-pass GroupNorm (opt-in: measured slower than the two-pass
-    kernels on L2-resident activations).  The switch is read once per process -> run in a child process."""
+    """The default GroupNorm is the two-pass (stats + apply) pair.  Two single-pass variants stay available as
+    opt-ins because both measured slower on the UNet shapes: PFD_GN_CLUSTER=1 (8-CTA thread-block cluster, slice
+    cached in shared memory, statistics reduced through distributed shared memory) and PFD_GN_FUSED=1 (grid-wide
+    arrival counter).  The switches are read once per process -> run in a child process."""
     import os
     import subprocess
     import sys
@@ -164,17 +167,22 @@ def test_groupnorm_single_pass_opt_in():
         "import torch, torch.nn.functional as F\n"
         "from pfd_b200 import native as nv\n"
         "torch.manual_seed(0)\n"
-        "x = (torch.randn(2, 32, 32, 320, device='cuda') * 2 + 0.5).half()\n"
-        "g = (torch.randn(320, device='cuda') + 1).half(); b = torch.randn(320, device='cuda').half()\n"
-        "nv.gn_reset()\n"
-        "o = nv.groupnorm(x, g, b, 1e-5, silu=True)\n"
-        "r = F.silu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, g.float(), b.float(), 1e-5)).permute(0, 2, 3, 1)\n"
-        "torch.testing.assert_close(o.float(), r, rtol=6e-3, atol=6e-3)\n"
+        "for (side, c1, c2) in [(32, 320, 0), (10, 640, 320), (8, 1280, 1280), (3, 320, 0), (64, 320, 0)]:\n"
+        "    x1 = (torch.randn(2, side, side, c1, device='cuda') * 2 + 0.5).half()\n"
+        "    x2 = torch.randn(2, side, side, c2, device='cuda').half() if c2 else None\n"
+        "    C = c1 + c2\n"
+        "    g = (torch.randn(C, device='cuda') + 1).half(); b = torch.randn(C, device='cuda').half()\n"
+        "    nv.gn_reset()\n"
+        "    o = nv.groupnorm(x1, g, b, 1e-5, silu=True, x2=x2)\n"
+        "    xc = x1 if x2 is None else torch.cat([x1, x2], 3)\n"
+        "    r = F.silu(F.group_norm(xc.float().permute(0, 3, 1, 2), 32, g.float(), b.float(), 1e-5)).permute(0, 2, 3, 1)\n"
+        "    torch.testing.assert_close(o.float(), r, rtol=6e-3, atol=6e-3)\n"
         "print('ok')\n")
-    env = dict(os.environ, PFD_GN_FUSED="1")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+    for extra in ({"PFD_GN_CLUSTER": "1"}, {"PFD_GN_FUSED": "1"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "ok" in r.stdout, (extra, r.stderr[-2000:])
 
 
 @pytest.mark.parametrize("C", [192, 320, 768, 1280, 1536])
