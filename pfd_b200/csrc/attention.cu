@@ -31,18 +31,6 @@ constexpr int FA_BQ = 128;
 constexpr int FA_BKV = 64;
 constexpr int FA_THREADS = 192;
 
-// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max rel. error 7.5e-5 - the fp16 P
-// operand resolves 4.9e-4): used for a fraction of the elements so that the MUFU pipe (58 % busy in the ncu
-// capture of the level-0 self-attention, the busiest pipe) is not the only producer of exponentials.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -30.f);                                    // 2^-30 rounds to 0 in fp16
-  const float xf = x + 12582912.f;                        // 1.5 * 2^23: round(x) sits in the low mantissa bits
-  const float f = x - (xf - 12582912.f);                  // [-0.5, 0.5]
-  float pl = fmaf(f, 0.05516102f, 0.24261291f);
-  pl = fmaf(pl, f, 0.69326254f);
-  pl = fmaf(pl, f, 0.99992796f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(xf) << 23));
-}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -63,7 +51,6 @@ struct alignas(64) FlashParams {
   CUtensorMap tmQ, tmK, tmV;
   int Nq, Nk, heads, d;
   int nblk;
-  int poly_exp;                // 1: every 4th exponential on the FMA pipe (PFD_FLASH_POLY=1)
   float scale;
   __half* out;
   long long o_sb, o_sq, o_sh;  // element strides: batch, query row, head
@@ -81,13 +68,18 @@ struct FlashCfg {
   static constexpr int NSB = DCH == 1 ? 1 : 2;
   // K/V smem stages
   //
-  static constexpr int NKV = 2;   // (1 stage -> 4 CTAs/SM was measured 55% slower: intra-CTA QK^T/softmax overlap matters more)
+  static constexpr int NKV = 2;   // K stages (1 stage was measured 55% slower: the QK^T of block j+1 must overlap softmax j)
+  // V^T stages: V_j is only needed by PV_j, a full softmax after K_j, so for d <= 64 one stage is enough and the
+  // CTA fits four to an SM (55 KB, 128 TMEM columns, <= 85 registers): 16 softmax warps hide each other's
+  // TMEM-load / MUFU / barrier phases better than 12
+  static constexpr int NVS = DCH == 1 ? 1 : 2;
+  static constexpr int MIN_CTAS = DCH == 1 ? 4 : 2;
   // V^T stage = dN rows x 128 B (dN = ceil16(d + 1), runtime) so d=80 still fits two CTAs per SM
-  static int smem_bytes(int dN) { return Q_BYTES + NKV * (K_BYTES + dN * 128) + NPB * P_BYTES + 1024 + 128; }
+  static int smem_bytes(int dN) { return Q_BYTES + NKV * K_BYTES + NVS * dN * 128 + NPB * P_BYTES + 1024 + 128; }
 };
 
 template <int DCH>
-__global__ void __launch_bounds__(FA_THREADS)
+__global__ void __launch_bounds__(FA_THREADS, FlashCfg<DCH>::MIN_CTAS)
 flash_attn_kernel(const __grid_constant__ FlashParams p) {
   using Cfg = FlashCfg<DCH>;
   extern __shared__ uint8_t smem_raw[];
@@ -101,20 +93,22 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   const uint32_t tmem_cols = need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u);
   const uint32_t sQ = base;
   const uint32_t sK = sQ + Cfg::Q_BYTES;                  // [2][K_BYTES]
-  const uint32_t sV = sK + Cfg::NKV * Cfg::K_BYTES;       // [NKV][V_BYTES]
-  const uint32_t sP = sV + Cfg::NKV * V_BYTES;
+  const uint32_t sV = sK + Cfg::NKV * Cfg::K_BYTES;       // [NVS][V_BYTES]
+  const uint32_t sP = sV + Cfg::NVS * V_BYTES;
   const uint32_t bars = sP + Cfg::NPB * Cfg::P_BYTES;
-  uint8_t* gP = gbase + Cfg::Q_BYTES + Cfg::NKV * Cfg::K_BYTES + Cfg::NKV * V_BYTES;
+  uint8_t* gP = gbase + Cfg::Q_BYTES + Cfg::NKV * Cfg::K_BYTES + Cfg::NVS * V_BYTES;
   const uint32_t bar_q = bars;
-  auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
-  auto bar_kv_empty = [&](int s) { return bars + 8u * (3 + s); };
+  auto bar_k_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto bar_k_empty = [&](int s) { return bars + 8u * (3 + s); };
+  auto bar_v_full = [&](int s) { return bars + 8u * (12 + s); };
+  auto bar_v_empty = [&](int s) { return bars + 8u * (14 + s); };
   auto bar_s_full = [&](int s) { return bars + 8u * (5 + s); };
   auto bar_s_free = [&](int s) { return bars + 8u * (7 + s); };
   const uint32_t bar_p_ready = bars + 8u * 9;
   const uint32_t bar_pv_done = bars + 8u * 10;
   const uint32_t tmem_slot = bars + 8u * 11;
   volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(
-      gbase + Cfg::Q_BYTES + Cfg::NKV * Cfg::K_BYTES + Cfg::NKV * V_BYTES + Cfg::NPB * Cfg::P_BYTES + 8 * 11);
+      gbase + Cfg::Q_BYTES + Cfg::NKV * Cfg::K_BYTES + Cfg::NVS * V_BYTES + Cfg::NPB * Cfg::P_BYTES + 8 * 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,8 +125,10 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   if (warp == 1 && lane == 0) {
     mbar_init(bar_q, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_kv_full(s), 1);
-      mbar_init(bar_kv_empty(s), 1);
+      mbar_init(bar_k_full(s), 1);
+      mbar_init(bar_k_empty(s), 1);
+      mbar_init(bar_v_full(s), 1);
+      mbar_init(bar_v_empty(s), 1);
       mbar_init(bar_s_full(s), 1);
       mbar_init(bar_s_free(s), 128);
     }
@@ -142,11 +138,11 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   }
   if (warp == 2) tmem_alloc_rt(tmem_slot, tmem_cols);
   if (warp >= 2) {
-    // rows d..dN-1 of both V^T stages are never written by TMA (its box has d rows): row d = ones, rest = 0
+    // rows d..dN-1 of the V^T stages are never written by TMA (its box has d rows): row d = ones, rest = 0
     uint8_t* gV = gbase + Cfg::Q_BYTES + Cfg::NKV * Cfg::K_BYTES;
     const int t = threadIdx.x - 64;
     const int per_stage = (dN - d) * 8;               // 16-byte granules
-    for (int i = t; i < Cfg::NKV * per_stage; i += 128) {
+    for (int i = t; i < Cfg::NVS * per_stage; i += 128) {
       const int st = i / per_stage, g = i % per_stage;
       const uint32_t word = (g < 8) ? 0x3C003C00u : 0u;
       *reinterpret_cast<uint4*>(gV + st * V_BYTES + d * 128 + g * 16) = make_uint4(word, word, word, word);
@@ -165,13 +161,26 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
     if (lane == 0) {
       mbar_expect_tx(bar_q, Cfg::Q_BYTES);
       for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * FA_BQ * 128, &p.tmQ, bar_q, c * 64, q0, hb, bb);
-      for (int j = 0; j < nblk; ++j) {
+      auto issue_K = [&](int j) {
         const int st = j % Cfg::NKV, u = j / Cfg::NKV;
-        if (u >= 1) mbar_wait(bar_kv_empty(st), (u - 1) & 1);
-        mbar_expect_tx(bar_kv_full(st), Cfg::K_BYTES + d * 128);
+        if (u >= 1) mbar_wait(bar_k_empty(st), (u - 1) & 1);          // QK^T of block j - NKV has read the stage
+        mbar_expect_tx(bar_k_full(st), Cfg::K_BYTES);
         for (int c = 0; c < DCH; ++c)
-          tma_load_4d(sK + st * Cfg::K_BYTES + c * FA_BKV * 128, &p.tmK, bar_kv_full(st), c * 64, j * FA_BKV, hb, bb);
-        tma_load_4d(sV + st * V_BYTES, &p.tmV, bar_kv_full(st), j * FA_BKV, 0, hb, bb);
+          tma_load_4d(sK + st * Cfg::K_BYTES + c * FA_BKV * 128, &p.tmK, bar_k_full(st), c * 64, j * FA_BKV, hb, bb);
+      };
+      auto issue_V = [&](int j) {
+        const int st = j % Cfg::NVS, u = j / Cfg::NVS;
+        if (u >= 1) mbar_wait(bar_v_empty(st), (u - 1) & 1);          // PV of block j - NVS has read the stage
+        mbar_expect_tx(bar_v_full(st), d * 128);
+        tma_load_4d(sV + st * V_BYTES, &p.tmV, bar_v_full(st), j * FA_BKV, 0, hb, bb);
+      };
+      // K runs one block ahead of V: K_{j+1} feeds the QK^T that overlaps softmax j, V_j is only needed by PV_j
+      issue_K(0);
+      issue_V(0);
+      if (nblk > 1) issue_K(1);
+      for (int j = 1; j < nblk; ++j) {
+        if (j + 1 < nblk) issue_K(j + 1);
+        issue_V(j);
       }
     }
   } else if (warp == 1) {
@@ -195,9 +204,10 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
           }
         }
         umma_commit(bar_s_full(sb));
+        umma_commit(bar_k_empty(st));
       };
       mbar_wait(bar_q, 0);
-      mbar_wait(bar_kv_full(0), 0);
+      mbar_wait(bar_k_full(0), 0);
       tc_fence_after();
       issue_S(0);
       for (int j = 0; j < nblk; ++j) {
@@ -205,26 +215,25 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
           if (j + 1 < nblk) {
             const int st = (j + 1) % Cfg::NKV, u = (j + 1) / Cfg::NKV;
             const int sb = (j + 1) % Cfg::NSB, us = (j + 1) / Cfg::NSB;
-            mbar_wait(bar_kv_full(st), u & 1);
+            mbar_wait(bar_k_full(st), u & 1);
             if (us >= 1) mbar_wait(bar_s_free(sb), (us - 1) & 1);
             tc_fence_after();
             issue_S(j + 1);
           }
         };
-        // two K/V stages: QK^T of block j+1 is issued before PV of block j (overlaps the softmax of j);
-        // one stage: K_{j+1} can only land after PV_j released the stage, so PV_j goes first
-        if (Cfg::NKV > 1) next_S();
+        // QK^T of block j+1 is issued before PV of block j (overlaps the softmax of j)
+        next_S();
         mbar_wait(bar_p_ready, j & 1);
+        const int st = j % Cfg::NVS;
+        mbar_wait(bar_v_full(st), (j / Cfg::NVS) & 1);
         tc_fence_after();
-        const int st = j % Cfg::NKV;
         const uint64_t ad = make_sw128_kmajor_desc(sP + (Cfg::NPB == 2 ? (j & 1) * Cfg::P_BYTES : 0));
         const uint64_t bd = make_sw128_kmajor_desc(sV + st * V_BYTES);
 #pragma unroll
         for (int s = 0; s < FA_BKV / 16; ++s)
           umma_f16(tmem_O, ad + 2u * s, bd + 2u * s, idesc_o, (j > 0 || s > 0) ? 1u : 0u);
-        umma_commit(bar_kv_empty(st));
+        umma_commit(bar_v_empty(st));
         umma_commit(bar_pv_done);
-        if (Cfg::NKV == 1) next_S();
       }
     }
   } else {
@@ -278,24 +287,12 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       const float nm = -mnew;
       // p = 2^(s * c2 - mref) -> packed fp16 (registers), overlapping PV_{j-1}
       uint32_t pk[FA_BKV / 2];
-      if (p.poly_exp) {
 #pragma unroll
-        for (int i = 0; i < FA_BKV / 2; ++i) {
-          const float t0 = fmaf(__uint_as_float(r[2 * i]), c2, nm);
-          const float t1 = fmaf(__uint_as_float(r[2 * i + 1]), c2, nm);
-          const float e0 = fast_exp2(t0);
-          const float e1 = (i & 1) ? poly_exp2(t1) : fast_exp2(t1);   // every 4th element on the FMA pipe
-          const __half2 h = __floats2half2_rn(e0, e1);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < FA_BKV / 2; ++i) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), c2, nm));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), c2, nm));
-          const __half2 h = __floats2half2_rn(e0, e1);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
-        }
+      for (int i = 0; i < FA_BKV / 2; ++i) {
+        const float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), c2, nm));
+        const float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), c2, nm));
+        const __half2 h = __floats2half2_rn(e0, e1);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
       }
       if (j > 0) {
         // single P buffer / running O: PV_{j-1} must have consumed P and finished accumulating
@@ -430,14 +427,6 @@ extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, 
   if (int rc = encode4d(&p.tmK, k, d, Nk, heads, B, k_strides[2], k_strides[1], k_strides[0], FA_BKV, "K")) return rc;
   if (int rc = encode4d(&p.tmV, vt, Nk, d, heads, B, vt_strides[2], vt_strides[1], vt_strides[0], (cuuint32_t)d, "V^T")) return rc;
   p.Nq = Nq; p.Nk = Nk; p.heads = heads; p.d = d;
-  {
-    static int poly = -1;
-    if (poly < 0) {
-      const char* e = getenv("PFD_FLASH_POLY");
-      poly = (e && e[0] == '1') ? 1 : 0;
-    }
-    p.poly_exp = poly;
-  }
   p.nblk = (Nk + FA_BKV - 1) / FA_BKV;
   p.scale = scale;
   p.out = static_cast<__half*>(out);
