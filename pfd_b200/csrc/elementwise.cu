@@ -733,12 +733,14 @@ __global__ void patchify_kernel(const T* __restrict__ x, int B, int C, int H, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// Single-pass GroupNorm(+SiLU) on a thread-block cluster.  One cluster of GNC_CS CTAs owns (image n, G consecutive
+// Single-pass GroupNorm(+SiLU), CS = 8: on a thread-block cluster.  One cluster of GNC_CS CTAs owns (image n, G consecutive
 // groups): CTA r keeps pixels [r*npc, (r+1)*npc) x (G*cpg channels) in shared memory, the group statistics are
 // reduced across the cluster through distributed shared memory (mean first, then the centred second moment from
 // the cached slice: numerically the textbook two-pass form in fp32), and the slice is normalised straight out of
 // shared memory.  One HBM read + one write and ONE launch per GroupNorm (the stats + apply pair cost two ~5 us
 // launch floors and a second read; the grid-wide spin barrier of gn_fused_kernel cost more than it saved).
+// CS = 1: the same kernel without any cross-CTA step - one CTA owns ALL pixels of (image n, G groups); used when
+// that slice fits in shared memory (8x8 .. 32x32 levels), where the two-pass pair is launch-latency bound.
 constexpr int GNC_CS = 8;         // portable maximum cluster size
 constexpr int GNC_THREADS = 512;
 
@@ -757,7 +759,8 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank
   return v;
 }
 
-__global__ void __launch_bounds__(GNC_THREADS, 1)
+template <int CS>
+__global__ void __launch_bounds__(GNC_THREADS, CS == 1 ? 2 : 1)
 gn_cluster_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int HW, int groups,
                   int G, int npc, const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
                   int silu, __half* __restrict__ out, float inv_cnt) {
@@ -767,8 +770,8 @@ gn_cluster_kernel(const __half* __restrict__ x1, int c1, const __half* __restric
   const int Cs = G * cpg;               // channels of this cluster (multiple of 8)
   const int ncv = Cs / 8;
   const int nsub = groups / G;
-  const uint32_t rank = cluster_rank();
-  const int cl = blockIdx.x / GNC_CS;
+  const uint32_t rank = CS > 1 ? cluster_rank() : 0u;
+  const int cl = blockIdx.x / CS;
   const int n = cl / nsub, gs = cl % nsub;
   const int c0 = gs * Cs;
   const int p0 = (int)rank * npc;
@@ -817,13 +820,21 @@ gn_cluster_kernel(const __half* __restrict__ x1, int c1, const __half* __restric
     s_part1[tid] = s_acc[tid];
     s_acc[tid] = 0.f;
   }
-  cluster_arrive_rel();
-  cluster_wait_acq();
+  if (CS > 1) {
+    cluster_arrive_rel();
+    cluster_wait_acq();
+  } else {
+    __syncthreads();
+  }
   if (tid < G) {
     float t = 0.f;
-    const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part1[tid]));
+    if (CS > 1) {
+      const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part1[tid]));
 #pragma unroll
-    for (int r = 0; r < GNC_CS; ++r) t += ld_dsmem_f32(la, (uint32_t)r);
+      for (int r = 0; r < CS; ++r) t += ld_dsmem_f32(la, (uint32_t)r);
+    } else {
+      t = s_part1[tid];
+    }
     s_mean[tid] = t * inv_cnt;
   }
   __syncthreads();
@@ -854,17 +865,25 @@ gn_cluster_kernel(const __half* __restrict__ x1, int c1, const __half* __restric
   }
   __syncthreads();
   if (tid < G) s_part2[tid] = s_acc[tid];
-  cluster_arrive_rel();
-  cluster_wait_acq();
+  if (CS > 1) {
+    cluster_arrive_rel();
+    cluster_wait_acq();
+  } else {
+    __syncthreads();
+  }
   if (tid < G) {
     float t = 0.f;
-    const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part2[tid]));
+    if (CS > 1) {
+      const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part2[tid]));
 #pragma unroll
-    for (int r = 0; r < GNC_CS; ++r) t += ld_dsmem_f32(la, (uint32_t)r);
+      for (int r = 0; r < CS; ++r) t += ld_dsmem_f32(la, (uint32_t)r);
+    } else {
+      t = s_part2[tid];
+    }
     s_rstd[tid] = rsqrtf(t * inv_cnt + eps);
   }
   // peers may read this CTA's partials until they pass this point: arrive now, wait right before exit
-  cluster_arrive_rel();
+  if (CS > 1) cluster_arrive_rel();
   __syncthreads();
   // ---- phase 3: normalise (+SiLU) straight out of shared memory
   if (active) {
@@ -895,7 +914,7 @@ gn_cluster_kernel(const __half* __restrict__ x1, int c1, const __half* __restric
       *reinterpret_cast<uint4*>(out + ((long long)n * HW + p0 + pix) * C + c) = o;
     }
   }
-  cluster_wait_acq();
+  if (CS > 1) cluster_wait_acq();
 }
 
 static inline bool gn_fused_enabled() {
@@ -947,6 +966,41 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
       cl_mode = (e && e[0] == '1') ? 1 : 0;
     }
     const int cpg = C / groups;
+    static int solo_mode = -1;
+    if (solo_mode < 0) {
+      // opt-in: measured slower than the two-pass pair as well (r1 gn_perf2.log: 1.24 vs 1.04 ms per evaluation;
+      // 64-256 CTAs walking a 40-100 KB slice three times lose to ~450 CTAs streaming at full bandwidth twice)
+      const char* e = getenv("PFD_GN_SOLO");
+      solo_mode = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (solo_mode == 1 && cpg >= 8 && HW <= (1 << 20)) {
+      // one CTA per (image, G groups): largest slice <= 100 KB (two CTAs per SM) that still gives >= 64 CTAs
+      const size_t slice_max = 100 * 1024;
+      int Gsel = 0;
+      for (int G = groups; G >= 1; --G) {
+        if (groups % G) continue;
+        const int Cs = G * cpg;
+        if (Cs % 8 || Cs / 8 > GNC_THREADS) continue;
+        if ((size_t)HW * (Cs / 8) * 16 > slice_max) continue;
+        Gsel = G;
+        if ((long long)NB * (groups / G) >= 64) break;
+      }
+      if (Gsel > 0) {
+        const int Cs = Gsel * cpg;
+        const size_t smem = (size_t)HW * (Cs / 8) * 16 + 5 * GN_MAX_GROUPS * sizeof(float);
+        static bool attr_set1 = false;
+        if (!attr_set1) {
+          cudaFuncSetAttribute(gn_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(slice_max + 5 * GN_MAX_GROUPS * sizeof(float)));
+          attr_set1 = true;
+        }
+        launch_k(gn_cluster_kernel<1>, dim3((unsigned)(NB * (groups / Gsel))), dim3(GNC_THREADS), smem, st,
+                 static_cast<const __half*>(x1), (int)c1, static_cast<const __half*>(x2), (int)c2, (int)HW, (int)groups,
+                 Gsel, (int)HW, static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps, (int)silu,
+                 static_cast<__half*>(out), (float)inv_cnt);
+        return check_launch("gn_solo");
+      }
+    }
     if (cl_mode == 1 && cpg >= 8 && HW >= GNC_CS && HW <= (1 << 24)) {
       const int npc = (int)((HW + GNC_CS - 1) / GNC_CS);
       const size_t slice_max = 200 * 1024;
@@ -964,7 +1018,7 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
         const size_t smem = (size_t)npc * (Cs / 8) * 16 + 5 * GN_MAX_GROUPS * sizeof(float);
         static bool attr_set = false;
         if (!attr_set) {
-          cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          cudaFuncSetAttribute(gn_cluster_kernel<GNC_CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)(slice_max + 5 * GN_MAX_GROUPS * sizeof(float)));
           attr_set = true;
         }
@@ -982,7 +1036,7 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = use_pdl() ? 2 : 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, gn_cluster_kernel, static_cast<const __half*>(x1), (int)c1,
+        cudaError_t le = cudaLaunchKernelEx(&cfg, gn_cluster_kernel<GNC_CS>, static_cast<const __half*>(x1), (int)c1,
                                             static_cast<const __half*>(x2), (int)c2, (int)HW, (int)groups, Gsel, npc,
                                             static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps,
                                             (int)silu, static_cast<__half*>(out), (float)inv_cnt);

@@ -156,10 +156,11 @@ def test_groupnorm(nv, C1, C2, HW, silu):
 
 
 def test_groupnorm_single_pass_opt_in():
-    """The default GroupNorm is the two-pass (stats + apply) pair.  Two single-pass variants stay available as
-    opt-ins because both measured slower on the UNet shapes: PFD_GN_CLUSTER=1 (8-CTA thread-block cluster, slice
-    cached in shared memory, statistics reduced through distributed shared memory) and PFD_GN_FUSED=1 (grid-wide
-    arrival counter).  The switches are read once per process -> run in a child process."""
+    """GroupNorm variants.  Default: the two-pass (stats + apply) pair.  Three single-pass variants stay available
+    as opt-ins because all of them measured slower on the UNet shapes (profiles/README.md): PFD_GN_SOLO=1 (one CTA
+    per (image, group set), slice cached in shared memory), PFD_GN_CLUSTER=1 (8-CTA thread-block cluster,
+    statistics reduced through distributed shared memory) and PFD_GN_FUSED=1 (grid-wide arrival counter).
+    The switches are read once per process -> child processes."""
     import os
     import subprocess
     import sys
@@ -179,7 +180,7 @@ def test_groupnorm_single_pass_opt_in():
         "    torch.testing.assert_close(o.float(), r, rtol=6e-3, atol=6e-3)\n"
         "print('ok')\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for extra in ({"PFD_GN_CLUSTER": "1"}, {"PFD_GN_FUSED": "1"}):
+    for extra in ({"PFD_GN_SOLO": "1"}, {"PFD_GN_CLUSTER": "1"}, {"PFD_GN_FUSED": "1"}):
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "ok" in r.stdout, (extra, r.stderr[-2000:])

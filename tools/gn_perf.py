@@ -1,4 +1,4 @@
-"""GroupNorm(+SiLU) device time on the UNet's shapes (graph-timed); run with PFD_GN_CLUSTER=0 for the two-pass kernels."""
+"""GroupNorm(+SiLU) device time on the UNet's shapes (graph-timed); default = two-pass kernels; PFD_GN_SOLO=1 / PFD_GN_CLUSTER=1 select the single-pass variants."""
 import json
 import os
 import sys
