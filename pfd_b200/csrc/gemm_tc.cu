@@ -1168,8 +1168,8 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   //      tiles of the CTA; requires n_tile fixed per CTA (grid = multiple of n_tiles).
   p.b_resident = 0;
   if (d->nseg == 1 && d->taps[0] == 1 && !p.b_batched && p.splits == 1 && gemm_bres_enabled()) {
-    const int try_bn[3] = {BNsel, 128, 64};
-    for (int i = 0; i < 3; ++i) {
+    const int try_bn[1] = {BNsel};     // (switching to a narrower tile to make the weights fit measured slower)
+    for (int i = 0; i < 1; ++i) {
       const int bn_c = try_bn[i];
       if (d->bn_force && bn_c != d->bn_force) continue;
       if (geglu && (d->N % bn_c)) continue;

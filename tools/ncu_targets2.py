@@ -1,4 +1,5 @@
-"""Second ncu driver: small-K linear, GEGLU projection, split-K 8x8 conv, flash attention (current build)."""
+"""ncu driver: small-K linear, GEGLU projection, 3x3 convs (32x32 1920->640, 64x64 320->320), split-K 8x8 conv,
+flash attention (level-0 self-attention) on the current build; two launches each (the second is L2-warm)."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,6 +18,16 @@ wgp, _, bn = nv.pack_geglu(wg, None)
 og = torch.empty(32768, 1280, device=dev, dtype=torch.float16)
 for _ in range(2):
     nv.linear(x, wgp, None, act=nv.ACT_GEGLU, out=og, bn_force=bn)
+xa = torch.randn(8, 32, 32, 1920, device=dev).half()
+wa = (torch.randn(640, 9 * 1920, device=dev) * (9 * 1920) ** -0.5).half()
+oa2 = torch.empty(8, 32, 32, 640, device=dev, dtype=torch.float16)
+for _ in range(2):
+    nv.conv3x3(xa, wa, b.new_zeros(640), out=oa2)
+xb = torch.randn(8, 64, 64, 320, device=dev).half()
+wb = (torch.randn(320, 9 * 320, device=dev) * (9 * 320) ** -0.5).half()
+ob2 = torch.empty(8, 64, 64, 320, device=dev, dtype=torch.float16)
+for _ in range(2):
+    nv.conv3x3(xb, wb, b, out=ob2)
 xc = torch.randn(8, 8, 8, 1280, device=dev).half()
 wc = (torch.randn(1280, 9 * 1280, device=dev) * (9 * 1280) ** -0.5).half()
 oc = torch.empty(8, 8, 8, 1280, device=dev, dtype=torch.float16)
