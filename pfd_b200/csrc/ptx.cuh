@@ -31,7 +31,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // of ns, and ncu showed ~27 % of the flash kernel's issued instructions were polling (SYNCS/BRA/YIELD/IADD3/
 // ISETP) competing with the softmax warps for issue slots.  The thread still resumes as soon as the phase
 // completes; the hint only bounds how long the hardware may keep it parked.
-constexpr uint32_t MBAR_SUSPEND_HINT_NS = 4096;
+#ifndef PFD_MBAR_HINT_NS
+#define PFD_MBAR_HINT_NS 4096
+#endif
+constexpr uint32_t MBAR_SUSPEND_HINT_NS = PFD_MBAR_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

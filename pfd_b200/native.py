@@ -16,7 +16,8 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfd_b200.so")
+# PFD_B200_LIB: load another build of the same ABI (A/B runs of compile-time variants); default = the in-tree library
+LIB_PATH = os.environ.get("PFD_B200_LIB") or os.path.join(_HERE, "libpfd_b200.so")
 
 PFD_MAX_SEG = 3
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_RELU, ACT_GEGLU = 0, 1, 2, 3, 4
