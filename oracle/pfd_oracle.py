@@ -633,9 +633,14 @@ def ddim_update(x, e_t, a_t, a_prev, sigma_t, sqrt_one_minus_at):
 def ddim_sample(unet_sd: SD, unet_cfg, alphas_cumprod: torch.Tensor, *, steps: int, x_T: torch.Tensor,
                 cond: torch.Tensor, uncond: Optional[torch.Tensor], guidance: float,
                 ctl_sd: Optional[SD] = None, ctl_cfg=None, hint: Optional[torch.Tensor] = None,
-                trace: Optional[list] = None, max_evals: Optional[int] = None) -> torch.Tensor:
-    """ddim.py:81-172 with eta = 0 and x_T supplied (the reference draws it with torch.randn, :105)."""
+                trace: Optional[list] = None, max_evals: Optional[int] = None,
+                n_forward: Optional[int] = None) -> torch.Tensor:
+    """ddim.py:81-172 with eta = 0 and x_T supplied (the reference draws it with torch.randn, :105).
+    n_forward: the img2img branch (ddim.py:94-101) - x_T is x0 already noised to timestep ts[n_forward] and only
+    the first n_forward timesteps are walked."""
     ts, alphas, alphas_prev, sigmas, s1m = ddim_schedule(alphas_cumprod, steps, 0.0)
+    if n_forward is not None:
+        ts = ts[:n_forward]
     x = x_T
     b = x.shape[0]
     total = ts.shape[0]

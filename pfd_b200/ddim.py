@@ -87,7 +87,15 @@ class DDIMSampler(object):
         if x_info.get("xt", None) is not None:
             x_T = x_info["xt"].to(device=device, dtype=torch.float16)
         elif x_info.get("x0", None) is not None:
-            raise NotImplementedError("img2img (x0) sampling is outside the pfd_b200 hot path (SURVEY.md §8f)")
+            # img2img branch (ddim.py:94-101): noise x0 forward to the n-th DDIM timestep (q_sample, pfd.py:204-207,
+            # same torch.randn_like RNG call) and run only the first n timesteps of the schedule
+            n_fwd = int(x_info["x0_forward_timesteps"])
+            x0 = x_info["x0"].to(device=device, dtype=torch.float16).contiguous()
+            t_fwd = int(timesteps[n_fwd])
+            timesteps = timesteps[:n_fwd]
+            noise = torch.randn_like(x0)
+            x_T = nv.axpby(x0, float(model.sqrt_alphas_cumprod[t_fwd]), noise,
+                           float(model.sqrt_one_minus_alphas_cumprod[t_fwd]))
         else:
             # same RNG call as ddim.py:105 (dtype of the conditioning; fp16 on the GPU path)
             x_T = torch.randn(shape, device=device, dtype=c_info["conditioning"].dtype).to(torch.float16)
@@ -111,7 +119,7 @@ class DDIMSampler(object):
                 if len(self._states) >= 2:
                     self._states.pop(next(iter(self._states)))
                 self._states[key] = st
-        st.load_request(x_T, c_full, cc, self._coef_table(device))
+        st.load_request(x_T, c_full, cc, self._coef_table(device)[:total])
         x = st.x
         intermediates = {"pred_xt": [], "pred_x0": []}
         for i, step in enumerate(np.flip(timesteps)):

@@ -218,6 +218,37 @@ def test_sampler_without_cfg_and_with_eta(env):
     assert torch.isfinite(xe.float()).all() and (xe.float() - x.float()).abs().max().item() > 1e-2
 
 
+def test_sampler_x0_img2img_branch(env):
+    """x_info['x0'] + 'x0_forward_timesteps' (ddim.py:94-101): x0 is noised forward with q_sample (same RNG call as
+    the reference) and only the first n DDIM timesteps are walked -> compare with the oracle on the same noise."""
+    net, gold, inp = env
+    from oracle import pfd_oracle as O
+    from pfd_b200 import DDIMSampler
+    cond = inp["cond"].half()
+    x0 = (inp["x_T"] * 0.5).half()
+    n_fwd, steps = 3, 6
+    torch.manual_seed(11)
+    x, _ = DDIMSampler(net).sample(steps=steps, x_info={"type": "image", "x0": x0, "x0_forward_timesteps": n_fwd},
+                                   c_info={"type": "image", "conditioning": cond, "unconditional_conditioning": None,
+                                           "unconditional_guidance_scale": 1.0, "control": None},
+                                   shape=[1, 4, 16, 16], verbose=False, eta=0.0)
+    torch.manual_seed(11)
+    noise = torch.randn_like(x0)
+    bufs = O.schedule_buffers()
+    ac16 = bufs["alphas_cumprod"].half().float()                      # the buffers are fp16 after net.half()
+    t_fwd = int(O.ddim_timesteps(steps)[n_fwd])
+    sa = float(net.sqrt_alphas_cumprod[t_fwd])
+    sb = float(net.sqrt_one_minus_alphas_cumprod[t_fwd])
+    x_T = sa * x0.float().cpu() + sb * noise.float().cpu()
+    sd = {k[len("diffuser.image."):]: v.detach().float().cpu() for k, v in net.state_dict().items()
+          if k.startswith("diffuser.image.")}
+    with torch.no_grad():
+        ref = O.ddim_sample(sd, O.UNET_SD15, bufs["alphas_cumprod"], steps=steps, x_T=x_T,
+                            cond=inp["cond"].cpu().half().float(), uncond=None, guidance=1.0, n_forward=n_fwd)
+    assert abs(float(ac16[t_fwd]) ** 0.5 - sa) < 2e-3
+    _check("ddim img2img branch (x0 noised to step 3 of 6)", x, ref, mse_tol=1e-3, rel_tol=2e-2)
+
+
 def test_native_library_is_what_ran():
     from pfd_b200 import native
     assert native.launch_count() > 0
