@@ -71,6 +71,16 @@ def test_schedule_buffers_and_ddim_timesteps():
     ts, a, ap, sg, s1m = O.ddim_schedule(buf["alphas_cumprod"], 50, 0.0)
     assert np.array_equal(s.ddim_timesteps, ts) and torch.equal(s.ddim_alphas, a)
     assert np.array_equal(s.ddim_alphas_prev, ap) and np.allclose(np.asarray(s.ddim_sqrt_one_minus_alphas), np.asarray(s1m))
+    # per-step coefficient table fed to pfd_ddim_step_f16: the fp16 roundings torch.full(..., dtype=float16) applies
+    tab = s._coef_table("cpu")
+    assert tab.shape == (50, 4) and tab.dtype == torch.float32
+    for i in (0, 17, 49):
+        want = [float(a[i].half()), float(torch.tensor(ap[i]).half()), 0.0, float(torch.as_tensor(s1m[i]).half())]
+        assert tab[i].tolist() == want
+    # eta > 0: sigma_t of ddim.py:44-48 lands in column 2; the img2img branch walks a prefix of the same table
+    s.make_schedule(50, ddim_eta=0.5)
+    _, a2, ap2, sg2, _ = O.ddim_schedule(buf["alphas_cumprod"], 50, 0.5)
+    assert np.allclose(np.asarray(s.ddim_sigmas), np.asarray(sg2)) and float(s._coef_table("cpu")[10, 2]) > 0.0
 
 
 def test_timestep_embedding_formula():
