@@ -196,7 +196,6 @@ def gemm_roofline_pass(net, sampler_cls, cond, uncond, batch, L):
 
     stats = {"flops": 0.0, "n": 0}
     orig = {"gemm_raw": nv.gemm_raw, "flash_attn": nv.flash_attn, "groupnorm": nv.groupnorm, "layernorm": nv.layernorm}
-    flash_names = ("flash_attn", "flash_attn_qkv")
 
     def counting(segs, **kw):
         stats["flops"] += 2.0 * kw["W"] * kw["H"] * kw["NB"] * kw["N"] * sum(t * c for (_, t, c, _) in segs)
@@ -213,14 +212,13 @@ def gemm_roofline_pass(net, sampler_cls, cond, uncond, batch, L):
     torch.cuda.synchronize()
 
     def graph_ms(skip=()):
-        skip = tuple(skip) + (("flash_attn_qkv", "flash_attn_strided") if "flash_attn" in skip else ())
+        skip = tuple(skip) + (("flash_attn_strided",) if "flash_attn" in skip else ())
         saved = {k: getattr(nv, k) for k in skip}
         try:
             if "gemm_raw" in skip:
                 nv.gemm_raw = lambda segs, **kw: None
             if "flash_attn" in skip:
                 nv.flash_attn = lambda q, k, vt, **kw: kw["out"]
-                nv.flash_attn_qkv = lambda q, k, v, **kw: kw["out"]
                 nv.flash_attn_strided = lambda q, k, vt, **kw: kw["out"]
             if "groupnorm" in skip:
                 def gn(x_, g_, b_, eps_, silu=False, x2=None, groups=32, out=None):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PFD_ABI_VERSION 1
+#define PFD_ABI_VERSION 2
 #if defined(__GNUC__)
 #define PFD_API __attribute__((visibility("default")))
 #else
@@ -50,7 +50,7 @@ PFD_API int64_t pfd_launch_count(void);
  * pfd_gemm_f16 — the tcgen05 tensor-core contraction used for every Linear, 1x1 conv, 3x3 conv
  * (implicit GEMM, TMA does the im2col) and batched QK^T / PV product on the path.
  *
- *   out[n, y, x, :] = act( alpha * sum_seg sum_tap sum_c A_seg[n, y*s+dy-1, x*s+dx-1, c] * Wt[:, k(seg,tap,c)]
+ *   out[n, y, x, :] = act( alpha * sum_seg sum_tap sum_c A_seg[n, y*s+dy-1+o, x*s+dx-1+o, c] * Wt[:, k(seg,tap,c)]
  *                          + bias + rowadd[n, :] ) + residual[n, y, x, :]
  *
  * Replaces: torch.nn.functional.conv2d / F.linear / torch.einsum / torch.bmm at
@@ -96,6 +96,8 @@ typedef struct pfd_gemm_desc {
   int64_t so_n1, so_n0, so_y, so_x, so_c1, so_c0;
   int32_t ndiv, cdiv;
   int32_t bn_force;          /* 0 = library picks the N tile; else one of 64/128/160/192/256 (GEGLU packing) */
+  int32_t tap_off;           /* 3x3 taps read A at (y*s + dy - 1 + tap_off): 0 = symmetric padding 1; 1 = the VAE
+                                encoder's F.pad(x,(0,1,0,1)) + stride-2 conv with padding 0 (autokl_modules.py:69-76) */
   void* stream;
 } pfd_gemm_desc;
 
@@ -139,9 +141,10 @@ PFD_API int pfd_timestep_embedding_f16(const int64_t* t, int32_t n, int32_t dim,
 PFD_API int pfd_upsample2x_f16(const void* x, int32_t NB, int32_t H, int32_t W, int32_t C, void* out,
                        void* stream);
 
-/* layout converts at the pipeline edges: NCHW fp16/fp32 <-> channel-last fp16 (with channel pad). */
+/* layout converts at the pipeline edges: NCHW fp16/fp32 <-> channel-last fp16 (with channel pad):
+ * out[n,y,x,c] = x[n,c,y,x]*mul + add for c < C, 0 for the pad channels (autokl.py:34: x*2-1). */
 PFD_API int pfd_nchw_to_nhwc_f16(const void* x, int32_t src_is_f32, int32_t NB, int32_t C, int32_t H,
-                         int32_t W, int32_t Cpad, void* out, void* stream);
+                         int32_t W, int32_t Cpad, float mul, float add, void* out, void* stream);
 /* out_nchw[n,c,y,x] = clamp(x[n,y,x,c]*mul + add, lo, hi) for c < C (autokl.py:47,53: (dec+1)/2, clamp) */
 PFD_API int pfd_nhwc_to_nchw_f16(const void* x, int32_t NB, int32_t C, int32_t H, int32_t W, int32_t Cpad,
                          float mul, float add, float lo, float hi, void* out, void* stream);
@@ -166,10 +169,26 @@ PFD_API int pfd_add_rowvec_f16(const void* a, const void* row, int64_t rows, int
  * eps: [2*B, ...] as [uncond | cond] halves of `half_n` elements each; coefficients are read from a
  * device table coef[step*4 + {0..3}] = {a_t, a_prev, sigma_t, sqrt_one_minus_at} (fp32) indexed by
  * the device-side int *step so that a captured CUDA graph can be replayed for every step.
+ * noise (optional, eta > 0, ddim.py:168-170): x_prev += sigma_t * noise * temperature with the reference's fp16
+ * rounding order.  log_tab (optional): int32 slot per schedule index (-1 = none); the step's x_prev / pred_x0
+ * are also stored at log_xt / log_x0 + slot*half_n (the `intermediates` lists, ddim.py:122-124).
  */
 PFD_API int pfd_ddim_step_f16(const void* eps, const void* x, int64_t half_n, float guidance,
                       const float* coef, const int32_t* step, void* x_prev, void* pred_x0,
-                      void* stream);
+                      const void* noise, float temperature, const int32_t* log_tab, void* log_xt,
+                      void* log_x0, void* stream);
+
+/* VAE encoder posterior (distributions.py:24-37, autokl.py:33-42, pfd.py:266-273): moments = channel-last
+ * [B,H,W,cpad] quant_conv output (mean | logvar in the first 2*zc channels); logvar clamped to [-30,20],
+ * std = exp(logvar/2), sample = scale*(mean + std*noise) with caller-drawn fp32 noise [B,zc,H,W] (NULL: mode).
+ * Outputs NCHW fp16 [B,zc,H,W]; each may be NULL. */
+PFD_API int pfd_vae_posterior_f16(const void* moments, int32_t B, int32_t zc, int32_t H, int32_t W, int32_t cpad,
+                                  const float* noise, float scale, void* mean, void* logvar, void* stdv,
+                                  void* sample, void* stream);
+
+/* Device-side loop header of one DDIM step (ddim.py:108-113): *step -= 1; t_out[0..nb) = ttab[*step].
+ * Lets one CUDA graph hold several (or all) steps of the sampling loop with no host work in between. */
+PFD_API int pfd_ddim_begin_step(int32_t* step, const int64_t* ttab, int64_t* t_out, int32_t nb, void* stream);
 
 /* Swin window plumbing on channel-last [B,H,W,C] (swin.py:269-304): pad + cyclic shift + window
  * partition in one gather (fwd) and the inverse scatter + crop (bwd). */
@@ -204,20 +223,24 @@ PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, const void*
                                        const int64_t* vt_strides, float scale, int64_t o_sb, int64_t o_sq,
                                        void* stream);
 
-/*
- * Flash attention v2: q / k / v are 4-D strided views [B, heads, N, d] (strides {batch, head, row} in elements,
- * d contiguous), so one projection GEMM can emit q|k|v (or k|v) side by side; V is read in its natural
- * [keys, d] layout (MN-major tcgen05 operand).  Same semantics / output layout as pfd_flash_attn_f16.
- */
-PFD_API int pfd_flash_attn_qkv_f16(const void* q, const void* k, const void* v, void* out, int32_t B,
-                                   int32_t heads, int32_t Nq, int32_t Nk, int32_t d, const int64_t* q_strides,
-                                   const int64_t* k_strides, const int64_t* v_strides, float scale,
-                                   int64_t o_sb, int64_t o_sq, void* stream);
-
 /* PatchEmbed gather (swin.py:479-489): NCHW image (fp16/fp32) -> [B, ceil(H/P), ceil(W/P), Kpad] rows in
  * the K order of the flattened conv weight [O, C*P*P]; zero padding for ragged H/W and K..Kpad. */
 PFD_API int pfd_patchify_f16(const void* x, int32_t src_is_f32, int32_t B, int32_t C, int32_t H,
                              int32_t W, int32_t P, int32_t Kpad, void* out, void* stream);
+
+/*
+ * ControlNet.preprocess(type='canny') on the GPU (controlnet.py:332-360 -> controlnet_annotator/canny/__init__.py:4-5,
+ * i.e. cv2.Canny(rgb_u8, low, high) with aperture 3 / L1 gradient, bit-exact): x is an NCHW [B,3,H,W] image in
+ * [0,1] (fp16 or fp32), quantised like ToPILImage (x.mul(255).byte()); out is float32 [B,3,H,W] with 1.0 on edge
+ * pixels (ToTensor + repeat(1,3,1,1)).  workspace: pfd_canny_workspace_bytes(B,H,W) bytes of device memory.
+ * The call synchronises `stream` (hysteresis runs until a host-visible fixed point): not graph-capturable.
+ * sweeps_out (optional, host): number of hysteresis sweeps that were needed.
+ */
+PFD_API int64_t pfd_canny_workspace_bytes(int32_t B, int32_t H, int32_t W);
+PFD_API int pfd_canny_f32(const void* x, int32_t src_is_f32, int32_t B, int32_t H, int32_t W, int32_t low,
+                          int32_t high, void* workspace, float* out, int32_t* sweeps_out, void* stream);
+/* ToTensor(ToPILImage(x)) = floor(x*255)/255 as float32 (controlnet.py:345-348, preprocess type 'input'). */
+PFD_API int pfd_image_u8_roundtrip_f32(const void* x, int32_t src_is_f32, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

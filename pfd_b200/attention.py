@@ -22,8 +22,6 @@ from . import native as nv
 # fused tcgen05 flash attention for bias-free attention; False falls back to the materialised
 # QK^T GEMM -> softmax -> PV GEMM pipeline (still all pfd_b200 kernels) — used by tests to cross-check.
 USE_FLASH = True
-# v2: fused q|k|v projection GEMM + strided / MN-major-V flash kernel (pfd_flash_attn_qkv_f16)
-USE_FLASH_V2 = False
 # fused q|k projection + V^T produced by a "swapped" GEMM (Wv . X^T), consumed by the v1 kernel through strided views
 USE_FUSED_QK = True
 
@@ -97,15 +95,6 @@ def project_heads_fused(x2d: torch.Tensor, w: torch.Tensor, b: Optional[torch.Te
     nv.gemm_raw([(x2d, 1, x2d.shape[1], (ld, ld * N, ld * N))], in_w=N, in_h=1, stride=1, W=N, H=1, NB=B, w=w,
                 N=w.shape[0], K=w.stride(0), bias=b, out=out, so=(vh * Np * d, 0, 0, d, Np * d, 1), ndiv=1, cdiv=d)
     return out
-
-
-def attend_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, Nq: int, Nk: int, scale: float,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Flash attention v2 on strided [B, heads, Np, d] views -> [B, Nq, heads*d]."""
-    B, heads, _, d = q.shape
-    if out is None:
-        out = torch.empty((B, Nq, heads * d), device=q.device, dtype=torch.float16)
-    return nv.flash_attn_qkv(q, k, v, Nq=Nq, Nk=Nk, scale=scale, out=out)
 
 
 def project_vt_swapped(x2d: torch.Tensor, wv: torch.Tensor, B: int, N: int, heads: int, d: int) -> torch.Tensor:

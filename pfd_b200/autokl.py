@@ -1,8 +1,9 @@
-"""AutoencoderKL (decode path) on the pfd_b200 kernels — mirrors lib/model_zoo/autokl.py:14-54 and
-lib/model_zoo/autokl_modules.py:82-202, 368-568.
+"""AutoencoderKL on the pfd_b200 kernels — mirrors lib/model_zoo/autokl.py:14-54 and
+lib/model_zoo/autokl_modules.py:59-202, 368-568.
 
-The Encoder's parameters are kept (same names/shapes) so that reference VAE checkpoints load with
-strict=True, but only `decode` is on the hot path; `encode` raises.
+`decode` is on the hot path; `encode` (img2img / image variation)
+runs the Encoder on the same kernels — its stride-2 downsampling convs use the reference's asymmetric
+F.pad(x, (0,1,0,1)) through the conv GEMM's `tap_off` (autokl_modules.py:69-76).
 """
 from __future__ import annotations
 
@@ -53,11 +54,14 @@ class _Resample(nn.Module):
 
 
 class Encoder(nn.Module):
-    """Parameter-only mirror of autokl_modules.py:368-459 (not on the hot path)."""
+    """autokl_modules.py:368-459."""
 
     def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
                  resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, **_):
         super().__init__()
+        if attn_resolutions:
+            raise NotImplementedError("pfd_b200 VAE encoder: attn_resolutions must be empty (autokl.yaml)")
+        self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
         self.conv_in = Conv2d(in_channels, ch, 3, padding=1)
         in_mult = (1,) + tuple(ch_mult)
         self.down = nn.ModuleList()
@@ -160,8 +164,41 @@ class AutoencoderKL(nn.Module):
         self.post_quant_conv = Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.embed_dim = embed_dim
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("VAE encode is outside the pfd_b200 hot path (SURVEY.md §8f)")
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, out_posterior: bool = False, post_scale: float = 1.0):
+        """autokl.py:30-42: x NCHW in [0,1] -> x*2-1 -> Encoder (autokl_modules.py:436-459) -> quant_conv ->
+        DiagonalGaussianDistribution -> posterior (out_posterior=True) or a sample [B, zc, H/8, W/8] (fp16;
+        `post_scale` carries the pipeline's latent scale, pfd.py:266-273).  The sample's noise is drawn like
+        the reference's: torch.randn(shape) on the CPU generator, then moved to the device."""
+        enc = self.encoder
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.to(torch.float16)
+        B = x.shape[0]
+        nv.gn_reset()
+        h = nv.nchw_to_nhwc(x, mul=2.0, add=-1.0)                          # [B,H,W,3]
+        w, b, kpad = pk_conv3_small(enc.conv_in)
+        _, H, W, _ = h.shape
+        h = nv.linear(nv.im2col3x3(h, kpad).reshape(B * H * W, kpad), w, b).reshape(B, H, W, w.shape[0])
+        for lvl in range(enc.num_resolutions):
+            for rb in enc.down[lvl].block:
+                h = run_vae_resnet(rb, h)
+            if lvl != enc.num_resolutions - 1:
+                w, b = pk_conv3(enc.down[lvl].downsample.conv)
+                h = nv.conv3x3(h, w, b, stride=2, tap_off=1)
+        h = run_vae_resnet(enc.mid.block_1, h)
+        h = run_vae_attn(enc.mid.attn_1, h)
+        h = run_vae_resnet(enc.mid.block_2, h)
+        g, b = pk_norm(enc.norm_out)
+        h = nv.groupnorm(h, g, b, enc.norm_out.eps, silu=True)
+        w, b = pk_conv3(enc.conv_out)                                      # [2*zc -> 8 rows]
+        h = nv.conv3x3(h, w, b)
+        wq, bq = pk_lin(self.quant_conv)
+        mom = nv.conv1x1(h, wq, bq)                                        # [B,h,w,8]: mean | logvar
+        zc = self.quant_conv.weight.shape[0] // 2
+        if out_posterior:
+            return DiagonalGaussianDistribution(mom, zc)
+        noise = torch.randn((B, zc, mom.shape[1], mom.shape[2])).to(mom.device)   # distributions.py:36
+        return nv.vae_posterior(mom, zc, noise=noise, scale=post_scale, want=("sample",))["sample"]
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor, pre_scale: float = 1.0) -> torch.Tensor:
@@ -194,6 +231,23 @@ class AutoencoderKL(nn.Module):
 
     def forward(self, z):
         return self.decode(z)
+
+
+class DiagonalGaussianDistribution(object):
+    """distributions.py:24-37 over the channel-last moments tensor; fields are NCHW fp16 tensors."""
+
+    def __init__(self, moments: torch.Tensor, zc: int):
+        self._mom, self._zc = moments, zc
+        o = nv.vae_posterior(moments, zc, want=("mean", "logvar", "std"))
+        self.mean, self.logvar, self.std = o["mean"], o["logvar"], o["std"]
+        self.deterministic = False
+
+    def sample(self):
+        noise = torch.randn(self.mean.shape).to(self.mean.device)        # distributions.py:36
+        return nv.vae_posterior(self._mom, self._zc, noise=noise, want=("sample",))["sample"]
+
+    def mode(self):
+        return self.mean
 
 
 def cached_conv_in(conv: Conv2d, cz: int):

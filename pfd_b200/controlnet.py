@@ -4,8 +4,8 @@ Same constructor arguments / state-dict keys as the reference (spatial-transform
 `legacy=False`).  ``forward`` returns the 13 residuals as channel-last tensors for
 ``UNetModel2D_Next.apply(control=...)``.  The hint stem (controlnet.py:165-181) depends only on the
 control image, so its output is cached per hint tensor instead of being recomputed every DDIM step.
-``preprocess`` (annotators, controlnet.py:332-503) is host-side image pre-processing outside the hot
-path and is not provided.
+``preprocess`` provides the annotator-free types on the GPU ('input', 'canny' — bit-exact cv2.Canny,
+SURVEY.md §8 f1); annotators that are networks of their own (controlnet.py:361-503) are outside the path.
 """
 from __future__ import annotations
 
@@ -161,9 +161,37 @@ class ControlNet(nn.Module):
         outs.append(nv.conv1x1(h, w, b))
         return outs
 
-    def preprocess(self, *a, **k):
-        raise NotImplementedError("controlnet annotators are host-side pre-processing outside the "
-                                  "pfd_b200 hot path; feed a ready control map (do_preprocess=False)")
+    @torch.no_grad()
+    def preprocess(self, x, type="canny", **kwargs):
+        """controlnet.py:332-360 for the annotator-free types: 'none', 'input' / 'shuffle_v11e' (the uint8 round
+        trip of ToPILImage -> ToTensor) and 'canny' / 'canny_v11p' (cv2.Canny(rgb_u8, low, high), reproduced
+        bit-exactly on the GPU by pfd_canny_f32).  x: [B,3,H,W] tensor in [0,1] or an image path.  Returns float32
+        [B,3,H,W] on x's device.  Annotators that are networks of their own (midas, hed, mlsd, openpose, ...) are
+        outside the hot path (SURVEY.md §8 f1 names Canny only)."""
+        if type == "none" or type is None:
+            return None
+        if isinstance(x, str):
+            import numpy as np
+            import PIL.Image
+            arr = np.array(PIL.Image.open(x).convert("RGB"))
+            x = torch.from_numpy(arr).permute(2, 0, 1)[None].to(self.get_device()).to(torch.float32) / 255.0
+        elif not isinstance(x, torch.Tensor):
+            raise AssertionError("preprocess expects a tensor or an image path")
+        if x.shape[1] == 1:
+            x = x.repeat(1, 3, 1, 1)
+        if not x.is_cuda:
+            x = x.to(self.get_device())
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.to(torch.float32)
+        if type in ("input", "shuffle_v11e"):
+            return nv.image_u8_roundtrip(x)
+        if type in ("canny", "canny_v11p"):
+            low = kwargs.pop("low_threshold", 100)
+            high = kwargs.pop("high_threshold", 200)
+            out, _ = nv.canny(x, int(low), int(high))
+            return out
+        raise NotImplementedError(f"controlnet annotator '{type}' is a separate network outside the pfd_b200 "
+                                  "hot path; feed a ready control map (do_preprocess=False)")
 
     def get_device(self):
         return self.time_embed[0].weight.device

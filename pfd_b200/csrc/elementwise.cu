@@ -221,145 +221,6 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   }
 }
 
-// Single-pass GroupNorm: each CTA keeps its pixel chunk in shared memory between the statistics phase and
-// the apply phase, so the activation is read from L2/HBM ONCE (the two-kernel version reads it twice) and
-// one launch disappears.  The phases are separated by a per-image arrival counter in global memory; this is
-// only used when every CTA of the grid can be co-resident (host checks with the occupancy API), and the
-// dependent kernel is not allowed to start launching before the barrier has been passed.
-__global__ void __launch_bounds__(320)
-gn_fused_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, long long HW,
-                int groups, const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
-                int silu, double* __restrict__ ws, unsigned int* __restrict__ counter, __half* __restrict__ out,
-                long long pix_per_cta, double inv_cnt) {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  extern __shared__ uint4 gn_tile[];
-  const int C = c1 + c2;
-  const int cpg = C / groups;
-  const int vecs = C / 8;
-  const int n = blockIdx.y;
-  const long long p0 = (long long)blockIdx.x * pix_per_cta;
-  long long p1 = p0 + pix_per_cta;
-  if (p1 > HW) p1 = HW;
-  __shared__ float s_sum[GN_MAX_GROUPS];
-  __shared__ float s_sq[GN_MAX_GROUPS];
-  if (threadIdx.x < GN_MAX_GROUPS) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
-  const int lanes = blockDim.x / vecs;          // host guarantees lanes >= 1 for this kernel
-  const int v = threadIdx.x % vecs;
-  const int c = v * 8;
-  const long long base = (long long)n * HW;
-  const bool active = threadIdx.x < lanes * vecs;
-  if (active) {
-    float sm[8], sq[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sm[i] = sq[i] = 0.f;
-    long long pix = p0 + threadIdx.x / vecs;
-    for (; pix + 3 * lanes < p1; pix += 4 * lanes) {
-      uint4 u[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = gn_load(x1, c1, x2, c2, base + pix + k * lanes, c);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        gn_tile[(pix + k * lanes - p0) * vecs + v] = u[k];
-        float f[8];
-        unpack8(u[k], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          sm[i] += f[i];
-          sq[i] += f[i] * f[i];
-        }
-      }
-    }
-    for (; pix < p1; pix += lanes) {
-      const uint4 u = gn_load(x1, c1, x2, c2, base + pix, c);
-      gn_tile[(pix - p0) * vecs + v] = u;
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sm[i] += f[i];
-        sq[i] += f[i] * f[i];
-      }
-    }
-    int g_prev = c / cpg;
-    float as = 0.f, aq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (c + i) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&s_sum[g_prev], as);
-        atomicAdd(&s_sq[g_prev], aq);
-        as = aq = 0.f;
-        g_prev = g;
-      }
-      as += sm[i];
-      aq += sq[i];
-    }
-    atomicAdd(&s_sum[g_prev], as);
-    atomicAdd(&s_sq[g_prev], aq);
-  }
-  __syncthreads();
-  if (threadIdx.x < groups) {
-    atomicAdd(&ws[((long long)n * groups + threadIdx.x) * 2 + 0], (double)s_sum[threadIdx.x]);
-    atomicAdd(&ws[((long long)n * groups + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
-  }
-  // ---- per-image barrier over the gridDim.x CTAs of image n
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    atomicAdd(&counter[n], 1u);
-    unsigned int spins = 0;
-    while (*reinterpret_cast<volatile unsigned int*>(&counter[n]) < gridDim.x) {
-      __nanosleep(64);
-      if (++spins > (1u << 22)) asm volatile("trap;");
-    }
-    __threadfence();
-  }
-  __syncthreads();
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (!active) return;
-  // ---- apply from shared memory
-  float a8[8], b8[8];
-  {
-    float g8[8], be8[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + c)), g8);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c)), be8);
-    int gprev = -1;
-    float mean = 0.f, rstd = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (c + i) / cpg;
-      if (g != gprev) {
-        const double m = __ldcg(&ws[((long long)n * groups + g) * 2 + 0]) * inv_cnt;
-        double var = __ldcg(&ws[((long long)n * groups + g) * 2 + 1]) * inv_cnt - m * m;
-        if (var < 0) var = 0;
-        mean = (float)m;
-        rstd = rsqrtf((float)var + eps);
-        gprev = g;
-      }
-      a8[i] = rstd * g8[i];
-      b8[i] = be8[i] - mean * a8[i];
-    }
-  }
-  for (long long pix = p0 + threadIdx.x / vecs; pix < p1; pix += lanes) {
-    float f[8];
-    unpack8(gn_tile[(pix - p0) * vecs + v], f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float y = fmaf(f[i], a8[i], b8[i]);
-      if (silu) {
-        y = rh(y);
-        y = __fdividef(y, 1.f + __expf(-y));
-      }
-      f[i] = y;
-    }
-    *reinterpret_cast<uint4*>(out + (base + pix) * C + c) = pack8(f);
-  }
-}
-
 // ------------------------------------------------------------------------------------ LayerNorm
 // one warp per row; C % 8 == 0; row cached in registers (C <= 8*32*MAXV).
 template <int MAXV>
@@ -508,7 +369,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int NB, int H, in
 
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ x, int NB, int C, int H, int W, int Cpad,
-                                    __half* __restrict__ out) {
+                                    float mul, float add, __half* __restrict__ out) {
   pdl_enter();
   const long long total = (long long)NB * H * W * Cpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -520,7 +381,7 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ x, int NB, int C, int 
     const int y = (int)(p % H);
     const int n = (int)(p / H);
     float v = 0.f;
-    if (c < C) v = (float)x[(((long long)n * C + c) * H + y) * W + xw];
+    if (c < C) v = fmaf((float)x[(((long long)n * C + c) * H + y) * W + xw], mul, add);
     out[i] = __float2half_rn(v);
   }
 }
@@ -594,11 +455,57 @@ __global__ void add_rowvec_kernel(const uint4* __restrict__ a, const uint4* __re
   }
 }
 
+// DiagonalGaussianDistribution of the VAE encoder (distributions.py:24-37, autokl.py:33-42): moments are the
+// channel-last [B, H, W, 2*zc] quant_conv output (mean | logvar); logvar is clamped to [-30, 20], std = exp(0.5 *
+// logvar); sample = scale * (mean + std * noise).  Outputs are NCHW [B, zc, H, W]; any output may be NULL.
+__global__ void vae_posterior_kernel(const __half* __restrict__ mom, int B, int zc, int H, int W, int cpad,
+                                     const float* __restrict__ noise, float scale, __half* __restrict__ mean,
+                                     __half* __restrict__ logvar, __half* __restrict__ stdv,
+                                     __half* __restrict__ sample) {
+  pdl_enter();
+  const long long total = (long long)B * zc * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int xw = (int)(i % W);
+    long long p = i / W;
+    const int y = (int)(p % H);
+    p /= H;
+    const int c = (int)(p % zc);
+    const int n = (int)(p / zc);
+    const __half* m = mom + (((long long)n * H + y) * W + xw) * cpad;
+    const float mu = __half2float(m[c]);
+    const float lv = fminf(fmaxf(__half2float(m[zc + c]), -30.f), 20.f);
+    const float sd = rh(__expf(0.5f * lv));
+    if (mean) mean[i] = __float2half_rn(mu);
+    if (logvar) logvar[i] = __float2half_rn(lv);
+    if (stdv) stdv[i] = __float2half_rn(sd);
+    if (sample) sample[i] = __float2half_rn(scale * fmaf(sd, noise ? noise[i] : 0.f, mu));
+  }
+}
+
+// Start of one DDIM step inside a replayed CUDA graph: the device-side step counter walks the schedule backwards
+// (ddim.py:108-112: index = total - i - 1) and the timestep of that index is broadcast to the UNet's t input
+// (ddim.py:113 torch.full((bs,), step)), so a graph holding any number of steps needs no host work between steps.
+__global__ void ddim_begin_step_kernel(int* __restrict__ step, const long long* __restrict__ ttab,
+                                       long long* __restrict__ t_out, int nb) {
+  pdl_enter();
+  const int idx = *step - 1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) t_out[i] = ttab[idx < 0 ? 0 : idx];
+  if (threadIdx.x == 0) *step = idx;
+}
+
 // CFG combine + DDIM update with the reference's fp16 rounding sequence (ddim.py:150-171).
+// noise (optional, eta > 0): x_prev = a_prev.sqrt()*pred_x0 + dir_xt + sigma_t*noise*temperature, every product /
+// sum rounded to fp16 in the reference's evaluation order (ddim.py:166-170).
+// log_tab (optional): slot per schedule index (-1 = not logged) of the `intermediates` lists (ddim.py:122-124);
+// the step's x_prev / pred_x0 are also written to log_xt / log_x0 [slot] so multi-step graphs need no host copy.
 __global__ void ddim_step_kernel(const __half* __restrict__ eps, const __half* __restrict__ x,
                                  long long half_n, float guidance, const float* __restrict__ coef,
                                  const int* __restrict__ step, __half* __restrict__ x_prev,
-                                 __half* __restrict__ pred_x0) {
+                                 __half* __restrict__ pred_x0, const __half* __restrict__ noise,
+                                 float temperature, const int* __restrict__ log_tab,
+                                 __half* __restrict__ log_xt, __half* __restrict__ log_x0) {
   pdl_enter();
   const int st = step ? *step : 0;
   // torch.full(..., dtype=fp16) rounds each coefficient to fp16 first (ddim.py:160-163)
@@ -609,6 +516,10 @@ __global__ void ddim_step_kernel(const __half* __restrict__ eps, const __half* _
   const float sqrt_at = rh(sqrtf(a_t));
   const float sqrt_ap = rh(sqrtf(a_prev));
   const float dir_c = rh(sqrtf(rh(rh(1.f - a_prev) - rh(sigma * sigma))));
+  const float temp = rh(temperature);
+  const int slot = log_tab ? log_tab[st] : -1;
+  __half* lxt = slot >= 0 ? log_xt + (long long)slot * half_n : nullptr;
+  __half* lx0 = slot >= 0 ? log_x0 + (long long)slot * half_n : nullptr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < half_n;
        i += (long long)gridDim.x * blockDim.x) {
     const float eu = __half2float(eps[i]);
@@ -618,9 +529,15 @@ __global__ void ddim_step_kernel(const __half* __restrict__ eps, const __half* _
     const float xv = __half2float(x[i]);
     const float p0 = rh(rh(xv - rh(s1m * e)) / sqrt_at);
     const float dir = rh(dir_c * e);
-    const float xp = rh(rh(sqrt_ap * p0) + dir);
-    x_prev[i] = __float2half_rn(xp);
-    if (pred_x0) pred_x0[i] = __float2half_rn(p0);
+    float xp = rh(rh(sqrt_ap * p0) + dir);
+    if (noise) xp = rh(xp + rh(rh(sigma * __half2float(noise[i])) * temp));
+    const __half xh = __float2half_rn(xp), p0h = __float2half_rn(p0);
+    x_prev[i] = xh;
+    if (pred_x0) pred_x0[i] = p0h;
+    if (lxt) {
+      lxt[i] = xh;
+      lx0[i] = p0h;
+    }
   }
 }
 
@@ -732,203 +649,6 @@ __global__ void patchify_kernel(const T* __restrict__ x, int B, int C, int H, in
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Single-pass GroupNorm(+SiLU), CS = 8: on a thread-block cluster.  One cluster of GNC_CS CTAs owns (image n, G consecutive
-// groups): CTA r keeps pixels [r*npc, (r+1)*npc) x (G*cpg channels) in shared memory, the group statistics are
-// reduced across the cluster through distributed shared memory (mean first, then the centred second moment from
-// the cached slice: numerically the textbook two-pass form in fp32), and the slice is normalised straight out of
-// shared memory.  One HBM read + one write and ONE launch per GroupNorm (the stats + apply pair cost two ~5 us
-// launch floors and a second read; the grid-wide spin barrier of gn_fused_kernel cost more than it saved).
-// CS = 1: the same kernel without any cross-CTA step - one CTA owns ALL pixels of (image n, G groups); used when
-// that slice fits in shared memory (8x8 .. 32x32 levels), where the two-pass pair is launch-latency bound.
-constexpr int GNC_CS = 8;         // portable maximum cluster size
-constexpr int GNC_THREADS = 512;
-
-__device__ __forceinline__ void cluster_arrive_rel() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acq() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
-  uint32_t ra;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-  return v;
-}
-
-template <int CS>
-__global__ void __launch_bounds__(GNC_THREADS, CS == 1 ? 2 : 1)
-gn_cluster_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int HW, int groups,
-                  int G, int npc, const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps,
-                  int silu, __half* __restrict__ out, float inv_cnt) {
-  extern __shared__ uint4 gnc_smem[];
-  const int C = c1 + c2;
-  const int cpg = C / groups;
-  const int Cs = G * cpg;               // channels of this cluster (multiple of 8)
-  const int ncv = Cs / 8;
-  const int nsub = groups / G;
-  const uint32_t rank = CS > 1 ? cluster_rank() : 0u;
-  const int cl = blockIdx.x / CS;
-  const int n = cl / nsub, gs = cl % nsub;
-  const int c0 = gs * Cs;
-  const int p0 = (int)rank * npc;
-  const int np = max(0, min(HW, p0 + npc) - p0);
-  uint4* slice = gnc_smem;
-  float* s_acc = reinterpret_cast<float*>(slice + (size_t)npc * ncv);   // [G] block accumulators
-  float* s_part1 = s_acc + GN_MAX_GROUPS;                                 // [G] this CTA's sum        (read by peers)
-  float* s_part2 = s_part1 + GN_MAX_GROUPS;                               // [G] this CTA's centred sq (read by peers)
-  float* s_mean = s_part2 + GN_MAX_GROUPS;
-  float* s_rstd = s_mean + GN_MAX_GROUPS;
-  const int tid = threadIdx.x;
-  if (tid < GN_MAX_GROUPS) s_acc[tid] = 0.f;
-  const int lanes = GNC_THREADS / ncv;      // >= 1 (ncv <= 320)
-  const int cv = tid % ncv;
-  const int lp = tid / ncv;
-  const bool active = lp < lanes;
-  const int c = c0 + cv * 8;                // global channel of this thread's vector
-  const int gl0 = (cv * 8) / cpg;           // first local group the vector touches
-  const int split = min(8, (gl0 + 1) * cpg - cv * 8);   // elements [0, split) belong to gl0, the rest to gl0 + 1
-  pdl_enter();
-  __syncthreads();
-  // ---- phase 1: load the slice, per-group sums
-  float a0 = 0.f, a1 = 0.f;
-  if (active) {
-    float sm[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sm[i] = 0.f;
-    for (int pix = lp; pix < np; pix += lanes) {
-      const uint4 u = gn_load(x1, c1, x2, c2, (long long)n * HW + p0 + pix, c);
-      slice[(size_t)pix * ncv + cv] = u;
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sm[i] += f[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < split) a0 += sm[i];
-      else a1 += sm[i];
-    }
-    atomicAdd(&s_acc[gl0], a0);
-    if (split < 8) atomicAdd(&s_acc[gl0 + 1], a1);
-  }
-  __syncthreads();
-  if (tid < G) {
-    s_part1[tid] = s_acc[tid];
-    s_acc[tid] = 0.f;
-  }
-  if (CS > 1) {
-    cluster_arrive_rel();
-    cluster_wait_acq();
-  } else {
-    __syncthreads();
-  }
-  if (tid < G) {
-    float t = 0.f;
-    if (CS > 1) {
-      const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part1[tid]));
-#pragma unroll
-      for (int r = 0; r < CS; ++r) t += ld_dsmem_f32(la, (uint32_t)r);
-    } else {
-      t = s_part1[tid];
-    }
-    s_mean[tid] = t * inv_cnt;
-  }
-  __syncthreads();
-  // ---- phase 2: centred second moment from the cached slice
-  if (active) {
-    const float m0 = s_mean[gl0];
-    const float m1 = split < 8 ? s_mean[gl0 + 1] : 0.f;
-    float q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = 0.f;
-    for (int pix = lp; pix < np; pix += lanes) {
-      float f[8];
-      unpack8(slice[(size_t)pix * ncv + cv], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float dlt = f[i] - (i < split ? m0 : m1);
-        q[i] = fmaf(dlt, dlt, q[i]);
-      }
-    }
-    a0 = a1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < split) a0 += q[i];
-      else a1 += q[i];
-    }
-    atomicAdd(&s_acc[gl0], a0);
-    if (split < 8) atomicAdd(&s_acc[gl0 + 1], a1);
-  }
-  __syncthreads();
-  if (tid < G) s_part2[tid] = s_acc[tid];
-  if (CS > 1) {
-    cluster_arrive_rel();
-    cluster_wait_acq();
-  } else {
-    __syncthreads();
-  }
-  if (tid < G) {
-    float t = 0.f;
-    if (CS > 1) {
-      const uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(&s_part2[tid]));
-#pragma unroll
-      for (int r = 0; r < CS; ++r) t += ld_dsmem_f32(la, (uint32_t)r);
-    } else {
-      t = s_part2[tid];
-    }
-    s_rstd[tid] = rsqrtf(t * inv_cnt + eps);
-  }
-  // peers may read this CTA's partials until they pass this point: arrive now, wait right before exit
-  if (CS > 1) cluster_arrive_rel();
-  __syncthreads();
-  // ---- phase 3: normalise (+SiLU) straight out of shared memory
-  if (active) {
-    float gm[8], bt[8], mu[8], rs[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + c)), gm);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c)), bt);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = i < split ? gl0 : gl0 + 1;
-      rs[i] = s_rstd[g] * gm[i];
-      mu[i] = bt[i] - s_mean[g] * rs[i];          // y = x * rs + mu
-    }
-    for (int pix = lp; pix < np; pix += lanes) {
-      float f[8];
-      unpack8(slice[(size_t)pix * ncv + cv], f);
-      uint4 o;
-      __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float y0 = fmaf(f[2 * i], rs[2 * i], mu[2 * i]);
-        float y1 = fmaf(f[2 * i + 1], rs[2 * i + 1], mu[2 * i + 1]);
-        if (silu) {
-          y0 = __fdividef(y0, 1.f + __expf(-y0));
-          y1 = __fdividef(y1, 1.f + __expf(-y1));
-        }
-        oh[i] = __floats2half2_rn(y0, y1);
-      }
-      *reinterpret_cast<uint4*>(out + ((long long)n * HW + p0 + pix) * C + c) = o;
-    }
-  }
-  if (CS > 1) cluster_wait_acq();
-}
-
-static inline bool gn_fused_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    // measured (r1 bench10 vs bench9): the activations are L2-resident between the two passes, so the
-    // cooperative single-pass kernel's per-image barrier costs more than the second read saves
-    // (1.31 vs 1.18 ms per UNet evaluation) -> opt-in only.
-    const char* e = getenv("PFD_GN_FUSED");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 static inline int grid_for(long long total, int threads) {
   long long g = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -956,127 +676,7 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   int threads = vecs <= 320 ? (vecs <= 256 ? (256 / vecs) * vecs : vecs) : 256;
   if (threads < 64) threads = vecs * ((64 + vecs - 1) / vecs);
   const double inv_cnt = 1.0 / ((double)HW * (C / groups));
-  // ---- single-pass cluster path: one 8-CTA cluster per (image, G groups), slice cached in shared memory
-  {
-    static int cl_mode = -1;       // -1 unknown, 0 off, 1 on
-    if (cl_mode < 0) {
-      // opt-in: correct, but measured ~2x slower than the two-pass kernels on every UNet shape (r1 gn_perf.log:
-      // 1.91 vs 1.04 ms per evaluation) - cluster launches of 8 x 512 threads cost more than the second read saves
-      const char* e = getenv("PFD_GN_CLUSTER");
-      cl_mode = (e && e[0] == '1') ? 1 : 0;
-    }
-    const int cpg = C / groups;
-    static int solo_mode = -1;
-    if (solo_mode < 0) {
-      // opt-in: measured slower than the two-pass pair as well (r1 gn_perf2.log: 1.24 vs 1.04 ms per evaluation;
-      // 64-256 CTAs walking a 40-100 KB slice three times lose to ~450 CTAs streaming at full bandwidth twice)
-      const char* e = getenv("PFD_GN_SOLO");
-      solo_mode = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (solo_mode == 1 && cpg >= 8 && HW <= (1 << 20)) {
-      // one CTA per (image, G groups): largest slice <= 100 KB (two CTAs per SM) that still gives >= 64 CTAs
-      const size_t slice_max = 100 * 1024;
-      int Gsel = 0;
-      for (int G = groups; G >= 1; --G) {
-        if (groups % G) continue;
-        const int Cs = G * cpg;
-        if (Cs % 8 || Cs / 8 > GNC_THREADS) continue;
-        if ((size_t)HW * (Cs / 8) * 16 > slice_max) continue;
-        Gsel = G;
-        if ((long long)NB * (groups / G) >= 64) break;
-      }
-      if (Gsel > 0) {
-        const int Cs = Gsel * cpg;
-        const size_t smem = (size_t)HW * (Cs / 8) * 16 + 5 * GN_MAX_GROUPS * sizeof(float);
-        static bool attr_set1 = false;
-        if (!attr_set1) {
-          cudaFuncSetAttribute(gn_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(slice_max + 5 * GN_MAX_GROUPS * sizeof(float)));
-          attr_set1 = true;
-        }
-        launch_k(gn_cluster_kernel<1>, dim3((unsigned)(NB * (groups / Gsel))), dim3(GNC_THREADS), smem, st,
-                 static_cast<const __half*>(x1), (int)c1, static_cast<const __half*>(x2), (int)c2, (int)HW, (int)groups,
-                 Gsel, (int)HW, static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps, (int)silu,
-                 static_cast<__half*>(out), (float)inv_cnt);
-        return check_launch("gn_solo");
-      }
-    }
-    if (cl_mode == 1 && cpg >= 8 && HW >= GNC_CS && HW <= (1 << 24)) {
-      const int npc = (int)((HW + GNC_CS - 1) / GNC_CS);
-      const size_t slice_max = 200 * 1024;
-      int Gsel = 0;
-      for (int G = groups; G >= 1; --G) {
-        if (groups % G) continue;
-        const int Cs = G * cpg;
-        if (Cs % 8 || Cs / 8 > GNC_THREADS) continue;
-        if ((size_t)npc * (Cs / 8) * 16 > slice_max) continue;
-        Gsel = G;                                                   // valid; keep shrinking until the machine is filled
-        if ((long long)NB * (groups / G) * GNC_CS >= num_sms()) break;
-      }
-      if (Gsel > 0) {
-        const int Cs = Gsel * cpg;
-        const size_t smem = (size_t)npc * (Cs / 8) * 16 + 5 * GN_MAX_GROUPS * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-          cudaFuncSetAttribute(gn_cluster_kernel<GNC_CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(slice_max + 5 * GN_MAX_GROUPS * sizeof(float)));
-          attr_set = true;
-        }
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((long long)NB * (groups / Gsel) * GNC_CS));
-        cfg.blockDim = dim3(GNC_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = GNC_CS;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = use_pdl() ? 2 : 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, gn_cluster_kernel<GNC_CS>, static_cast<const __half*>(x1), (int)c1,
-                                            static_cast<const __half*>(x2), (int)c2, (int)HW, (int)groups, Gsel, npc,
-                                            static_cast<const __half*>(gamma), static_cast<const __half*>(beta), eps,
-                                            (int)silu, static_cast<__half*>(out), (float)inv_cnt);
-        if (le == cudaSuccess) return check_launch("gn_cluster");
-        (void)cudaGetLastError();     // cluster launch rejected on this device/config: use the two-pass kernels
-        cl_mode = 0;
-      }
-    }
-  }
   if (zero_ws) cudaMemsetAsync(dws, 0, sizeof(double) * 2 * NB * groups, st);
-  // ---- single-pass path (chunk cached in shared memory, per-image arrival barrier) when the whole grid can be
-  //      co-resident; counters live right behind the fp64 sums in the (pre-zeroed) scratch slot
-  if (!zero_ws && vecs <= 320 && gn_fused_enabled()) {
-    const int lanes = threads / vecs;
-    static int max_smem_set = 0;
-    const size_t smem_cap = 96 * 1024;
-    long long ppc_f = (long long)(smem_cap / ((size_t)C * 2));
-    ppc_f = (ppc_f / lanes) * lanes;
-    if (ppc_f > HW) ppc_f = ((HW + lanes - 1) / lanes) * lanes;
-    if (ppc_f >= 4 * lanes) {
-      const size_t smem = (size_t)ppc_f * C * 2;
-      if (!max_smem_set) {
-        cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
-        max_smem_set = 1;
-      }
-      int per_sm = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, threads, smem);
-      // shrink the chunk (more CTAs) while everything still fits, to fill the machine
-      long long chunks_f = (HW + ppc_f - 1) / ppc_f;
-      const long long cap = (long long)per_sm * num_sms();
-      if (per_sm > 0 && chunks_f * NB <= cap) {
-        unsigned int* counter = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + (size_t)NB * groups * 16);
-        dim3 gridf((unsigned)chunks_f, (unsigned)NB);
-        launch_k(gn_fused_kernel, gridf, dim3(threads), smem, st, static_cast<const __half*>(x1), c1,
-                 static_cast<const __half*>(x2), c2, (long long)HW, groups, static_cast<const __half*>(gamma),
-                 static_cast<const __half*>(beta), eps, silu, dws, counter, static_cast<__half*>(out), ppc_f, inv_cnt);
-        return check_launch("gn_fused");
-      }
-    }
-  }
   // ~3 CTAs per SM, but at least 16 pixels per pixel-lane so the per-CTA setup is amortised
   long long chunks = (3LL * num_sms() + NB - 1) / NB;
   long long ppc = (HW + chunks - 1) / chunks;
@@ -1153,13 +753,13 @@ extern "C" PFD_API int pfd_upsample2x_f16(const void* x, int32_t NB, int32_t H, 
 }
 
 extern "C" PFD_API int pfd_nchw_to_nhwc_f16(const void* x, int32_t src_is_f32, int32_t NB, int32_t C, int32_t H,
-                                    int32_t W, int32_t Cpad, void* out, void* stream) {
+                                    int32_t W, int32_t Cpad, float mul, float add, void* out, void* stream) {
   const long long total = (long long)NB * H * W * Cpad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (src_is_f32)
-    launch_k(nchw_to_nhwc_kernel<float>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, static_cast<const float*>(x), NB, C, H, W, Cpad, static_cast<__half*>(out));
+    launch_k(nchw_to_nhwc_kernel<float>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, static_cast<const float*>(x), NB, C, H, W, Cpad, mul, add, static_cast<__half*>(out));
   else
-    launch_k(nchw_to_nhwc_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, static_cast<const __half*>(x), NB, C, H, W, Cpad, static_cast<__half*>(out));
+    launch_k(nchw_to_nhwc_kernel<__half>, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), st, static_cast<const __half*>(x), NB, C, H, W, Cpad, mul, add, static_cast<__half*>(out));
   return check_launch("nchw_to_nhwc");
 }
 
@@ -1198,11 +798,35 @@ extern "C" PFD_API int pfd_add_rowvec_f16(const void* a, const void* row, int64_
 
 extern "C" PFD_API int pfd_ddim_step_f16(const void* eps, const void* x, int64_t half_n, float guidance,
                                  const float* coef, const int32_t* step, void* x_prev, void* pred_x0,
-                                 void* stream) {
-  launch_k(ddim_step_kernel, dim3(grid_for(half_n, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
+                                 const void* noise, float temperature, const int32_t* log_tab, void* log_xt,
+                                 void* log_x0, void* stream) {
+  if (!eps || !x || !x_prev || !coef || half_n <= 0) return set_error("pfd_ddim_step_f16: null/empty argument");
+  if (log_tab && (!log_xt || !log_x0)) return set_error("pfd_ddim_step_f16: log_tab without log buffers");
+  launch_k(ddim_step_kernel, dim3(grid_for(half_n, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream),
       static_cast<const __half*>(eps), static_cast<const __half*>(x), half_n, guidance, coef, step,
-      static_cast<__half*>(x_prev), static_cast<__half*>(pred_x0));
+      static_cast<__half*>(x_prev), static_cast<__half*>(pred_x0), static_cast<const __half*>(noise), temperature,
+      log_tab, static_cast<__half*>(log_xt), static_cast<__half*>(log_x0));
   return check_launch("ddim_step");
+}
+
+extern "C" PFD_API int pfd_vae_posterior_f16(const void* moments, int32_t B, int32_t zc, int32_t H, int32_t W,
+                                             int32_t cpad, const float* noise, float scale, void* mean,
+                                             void* logvar, void* stdv, void* sample, void* stream) {
+  if (!moments || B <= 0 || zc <= 0 || cpad < 2 * zc) return set_error("pfd_vae_posterior_f16: bad arguments");
+  const long long total = (long long)B * zc * H * W;
+  launch_k(vae_posterior_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream),
+      static_cast<const __half*>(moments), (int)B, (int)zc, (int)H, (int)W, (int)cpad, noise, scale,
+      static_cast<__half*>(mean), static_cast<__half*>(logvar), static_cast<__half*>(stdv), static_cast<__half*>(sample));
+  return check_launch("vae_posterior");
+}
+
+extern "C" PFD_API int pfd_ddim_begin_step(int32_t* step, const int64_t* ttab, int64_t* t_out, int32_t nb,
+                                           void* stream) {
+  if (!step || !ttab || !t_out || nb <= 0) return set_error("pfd_ddim_begin_step: null/empty argument");
+  launch_k(ddim_begin_step_kernel, dim3(1), dim3(64), (size_t)(0), static_cast<cudaStream_t>(stream),
+      reinterpret_cast<int*>(step), reinterpret_cast<const long long*>(ttab), reinterpret_cast<long long*>(t_out),
+      (int)nb);
+  return check_launch("ddim_begin_step");
 }
 
 extern "C" PFD_API int pfd_window_gather_f16(const void* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t ws,

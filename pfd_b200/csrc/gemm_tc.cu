@@ -14,7 +14,6 @@
 #include <math.h>
 #include <string.h>
 
-#include <map>
 #include <mutex>
 
 #include "../../include/pfd_b200.h"
@@ -42,6 +41,7 @@ struct alignas(64) GemmParams {
   int chunks[PFD_MAX_SEG];
   int a_c[PFD_MAX_SEG];
   int stride;
+  int tap_off;
   int bw, bh, bn;
   int tiles_w, tiles_h, tiles_nb, n_tiles;
   int W, H, NB, N;
@@ -254,8 +254,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         for (int s = 0; s < p.nseg; ++s) {
           const int ntap = p.taps[s];
           for (int t = 0; t < ntap; ++t) {
-            const int dy = (ntap == 9) ? (t / 3 - 1) : 0;
-            const int dx = (ntap == 9) ? (t % 3 - 1) : 0;
+            const int dy = (ntap == 9) ? (t / 3 - 1 + p.tap_off) : 0;
+            const int dx = (ntap == 9) ? (t % 3 - 1 + p.tap_off) : 0;
             for (int j = 0; j < p.chunks[s]; ++j, ++kbi) {
               if (kbi < kb_begin || kbi >= kb_end) continue;
               mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -925,22 +925,32 @@ static inline bool gemm_bres_enabled() {
 }
 
 constexpr size_t SPLITK_WS_BYTES = 64ull << 20;
+// One fp32 split-K workspace per DEVICE, allocated by the first pfd_gemm_f16 call on that device that is not
+// inside a stream capture (cudaMalloc is illegal while capturing) - i.e. in the eager warm-up pass that every
+// graph-captured path of this package runs first - and then shared by the eager and the captured launches, so
+// that graph replay and eager execution choose the same split configuration (r1 advisor finding: the old
+// per-stream map was always empty on torch's capture stream, silently disabling split-K in every replayed path).
+// Launches of one device are stream-ordered by the callers (one request at a time), so one buffer
+// per device is enough.
 static float* splitk_workspace(cudaStream_t st) {
-  // one workspace per stream (calls on distinct streams may run concurrently); allocated on first use,
-  // which happens in the eager warm-up pass that precedes any CUDA-graph capture.
+  constexpr int MAX_DEV = 64;
   static std::mutex mu;
-  static std::map<cudaStream_t, float*> ws;
+  static float* ws[MAX_DEV] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
   std::lock_guard<std::mutex> lk(mu);
-  auto it = ws.find(st);
-  if (it != ws.end()) return it->second;
+  if (ws[dev]) return ws[dev];
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return nullptr;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
   float* pnew = nullptr;
   if (cudaMalloc(&pnew, SPLITK_WS_BYTES) != cudaSuccess) {
     (void)cudaGetLastError();
     return nullptr;
   }
-  ws[st] = pnew;
+  ws[dev] = pnew;
   return pnew;
 }
 
@@ -1036,6 +1046,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   if (d->K % 8) return set_error("pfd_gemm_f16: K pitch %lld must be a multiple of 8", (long long)d->K);
   if (d->W <= 0 || d->H <= 0 || d->NB <= 0) return set_error("pfd_gemm_f16: empty output raster");
   if (d->stride != 1 && d->stride != 2) return set_error("pfd_gemm_f16: stride %d unsupported", d->stride);
+  if (d->tap_off != 0 && d->tap_off != 1) return set_error("pfd_gemm_f16: tap_off %d unsupported", d->tap_off);
   if (!d->out || !d->b_ptr) return set_error("pfd_gemm_f16: null out/b pointer");
   long long ktot = 0;
   for (int s = 0; s < d->nseg; ++s) {
@@ -1054,6 +1065,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   memset(&p, 0, sizeof(p));
   p.nseg = d->nseg;
   p.stride = d->stride;
+  p.tap_off = d->tap_off;
   p.W = d->W; p.H = d->H; p.NB = d->NB; p.N = d->N;
   p.b_batched = d->b_batch_stride != 0;
   p.alpha = d->alpha;
@@ -1133,6 +1145,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   p.num_kb = num_kb;
   p.kb_per_split = num_kb;
   cudaStream_t st = static_cast<cudaStream_t>(d->stream);
+  float* const skws = splitk_workspace(st);     // allocated by the first eager call on this device
   // ---- split-K for long-K problems that cannot fill the machine (8x8-level convs): fewer, wider N tiles
   //      (less A re-read through L2) x several K slices, fp32 partials reduced by splitk_finish_kernel.
   if (!geglu && !d->bn_force && num_kb >= 32) {
@@ -1151,7 +1164,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
       if (splits > num_kb / 8) splits = num_kb / 8;
       const size_t need = (size_t)splits * (size_t)m_tiles * BM * (size_t)d->N * sizeof(float);
       if (splits >= 2 && need <= SPLITK_WS_BYTES) {
-        float* ws = splitk_workspace(st);
+        float* ws = skws;
         if (ws) {
           BNsel = bn_sk;
           p.n_tiles = (int)nt_sk;

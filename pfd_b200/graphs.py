@@ -14,11 +14,43 @@ import torch.nn as nn
 from . import native as nv
 
 
+_generation = 0
+
+
+def _bump_generation(*_a, **_k) -> None:
+    global _generation
+    _generation += 1
+
+
+def watch(module: nn.Module) -> None:
+    """Make `load_state_dict` on `module` (or any of its sub-modules) bump the process-wide weight generation,
+    which is folded into every graph / packed-weight signature: (data_ptr, _version) pairs alone can collide when
+    a module is rebuilt and the caching allocator hands out the same addresses (r1 advisor finding)."""
+    for m in module.modules():
+        if "_pfd_watched" not in m.__dict__:
+            m.__dict__["_pfd_watched"] = True
+            m.register_load_state_dict_post_hook(_bump_generation)
+
+
+def generation() -> int:
+    return _generation
+
+
+def invalidate(module: nn.Module = None) -> None:
+    """Explicitly drop every packed-weight cache under `module` and force graph re-capture — for callers that
+    modify weights behind autograd's version counter (e.g. `p.data.copy_(...)`)."""
+    _bump_generation()
+    if module is not None:
+        for m in module.modules():
+            m.__dict__.pop("_pfd_pk", None)
+
+
 def weights_signature(*modules: nn.Module) -> Tuple:
-    sig = []
+    sig = [_generation]
     for m in modules:
         if m is None:
             continue
+        watch(m)
         for p in m.parameters():
             sig.append((p.data_ptr(), p._version))
         for b in m.buffers():

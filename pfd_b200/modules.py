@@ -13,6 +13,8 @@ from typing import Callable, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
+from .graphs import generation, watch
+
 
 class _Holder:
     def forward(self, *a, **k):  # pragma: no cover
@@ -61,8 +63,12 @@ class IndexedSequential(nn.Sequential):
 # ------------------------------------------------------------------------------------------------
 def cached(mod: nn.Module, key: str, params: Sequence[Optional[torch.Tensor]], fn: Callable):
     """Memoise fn() on `mod` until any tensor in `params` is replaced or modified in place."""
-    store = mod.__dict__.setdefault("_pfd_pk", {})
-    sig = tuple((p.data_ptr(), p._version, p.device.index) if p is not None else None for p in params)
+    store = mod.__dict__.get("_pfd_pk")
+    if store is None:
+        store = mod.__dict__.setdefault("_pfd_pk", {})
+        watch(mod)
+    sig = (generation(),) + tuple((p.data_ptr(), p._version, p.device.index) if p is not None else None
+                                  for p in params)
     hit = store.get(key)
     if hit is None or hit[0] != sig:
         hit = (sig, fn())

@@ -28,7 +28,8 @@ EXPORTS = [
     "pfd_nchw_to_nhwc_f16", "pfd_nhwc_to_nchw_f16", "pfd_im2col3x3_f16", "pfd_axpby_f16",
     "pfd_add_rowvec_f16", "pfd_ddim_step_f16", "pfd_window_gather_f16", "pfd_window_scatter_f16",
     "pfd_patch_merge_gather_f16", "pfd_patchify_f16", "pfd_flash_attn_f16",
-    "pfd_flash_attn_qkv_f16", "pfd_flash_attn_strided_f16",
+    "pfd_flash_attn_strided_f16", "pfd_ddim_begin_step", "pfd_vae_posterior_f16",
+    "pfd_canny_workspace_bytes", "pfd_canny_f32", "pfd_image_u8_roundtrip_f32",
 ]
 
 
@@ -60,6 +61,7 @@ class GemmDesc(ctypes.Structure):
         ("so_c1", c_int64), ("so_c0", c_int64),
         ("ndiv", c_int32), ("cdiv", c_int32),
         ("bn_force", c_int32),
+        ("tap_off", c_int32),
         ("stream", c_void_p),
     ]
 
@@ -90,7 +92,9 @@ def load() -> ctypes.CDLL:
     lib.pfd_timestep_embedding_f16.argtypes = [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p]
     lib.pfd_upsample2x_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     lib.pfd_nchw_to_nhwc_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
-                                         c_void_p, c_void_p]
+                                         c_float, c_float, c_void_p, c_void_p]
+    lib.pfd_vae_posterior_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_float,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pfd_nhwc_to_nchw_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                          c_float, c_float, c_float, c_void_p, c_void_p]
     lib.pfd_im2col3x3_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
@@ -98,7 +102,7 @@ def load() -> ctypes.CDLL:
     lib.pfd_axpby_f16.argtypes = [c_void_p, c_float, c_void_p, c_float, c_int64, c_void_p, c_void_p]
     lib.pfd_add_rowvec_f16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     lib.pfd_ddim_step_f16.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_void_p]
+                                      c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pfd_window_gather_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                           c_void_p, c_void_p]
     lib.pfd_window_scatter_f16.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
@@ -111,12 +115,18 @@ def load() -> ctypes.CDLL:
         lib.pfd_flash_attn_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                            c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                            c_int64, c_int64, c_int64, c_int32, c_void_p]
-    lib.pfd_flash_attn_qkv_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
-                                           c_int32, c_int32, POINTER(c_int64), POINTER(c_int64),
-                                           POINTER(c_int64), c_float, c_int64, c_int64, c_void_p]
-    lib.pfd_flash_attn_strided_f16.argtypes = list(lib.pfd_flash_attn_qkv_f16.argtypes)
+    lib.pfd_flash_attn_strided_f16.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                               c_int32, c_int32, POINTER(c_int64), POINTER(c_int64),
+                                               POINTER(c_int64), c_float, c_int64, c_int64, c_void_p]
+    lib.pfd_ddim_begin_step.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.pfd_canny_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
+    lib.pfd_canny_workspace_bytes.restype = c_int64
+    lib.pfd_canny_f32.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                  POINTER(c_int32), c_void_p]
+    lib.pfd_image_u8_roundtrip_f32.argtypes = [c_void_p, c_int32, c_int64, c_void_p, c_void_p]
     for name in EXPORTS:
-        if hasattr(lib, name) and name not in ("pfd_version", "pfd_last_error", "pfd_launch_count"):
+        if hasattr(lib, name) and name not in ("pfd_version", "pfd_last_error", "pfd_launch_count",
+                                               "pfd_canny_workspace_bytes"):
             getattr(lib, name).restype = c_int32
     _lib = lib
     return lib
@@ -166,7 +176,7 @@ def gemm_raw(segs: Sequence[Tuple[torch.Tensor, int, int, Tuple[int, int, int]]]
              bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None,
              residual: Optional[torch.Tensor] = None, out: torch.Tensor,
              so: Tuple[int, int, int, int, int, int], ndiv: int = 1, cdiv: int = 0,
-             bn_force: int = 0) -> None:
+             bn_force: int = 0, tap_off: int = 0) -> None:
     """Lowest-level call: ``segs`` is a list of (tensor, taps, channels, (sx, sy, sn))."""
     d = GemmDesc()
     d.nseg = len(segs)
@@ -190,6 +200,7 @@ def gemm_raw(segs: Sequence[Tuple[torch.Tensor, int, int, Tuple[int, int, int]]]
     d.so_n1, d.so_n0, d.so_y, d.so_x, d.so_c1, d.so_c0 = so
     d.ndiv, d.cdiv = ndiv, cdiv
     d.bn_force = bn_force
+    d.tap_off = tap_off
     d.stream = stream_ptr()
     _check(load().pfd_gemm_f16(ctypes.byref(d)), "pfd_gemm_f16")
 
@@ -240,13 +251,14 @@ def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor]):
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1,
             rowadd: Optional[torch.Tensor] = None, act: int = ACT_NONE,
             residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-            skip: Sequence[torch.Tensor] = ()) -> torch.Tensor:
+            skip: Sequence[torch.Tensor] = (), tap_off: int = 0) -> torch.Tensor:
     """3x3 / pad 1 convolution on channel-last x [NB, H, W, C] with packed weights
     w [Cout, 9*C (+ sum of skip channels)] (k = tap*C + c, then the 1x1 skip-segment channels).
     ``skip`` tensors (same raster, stride 1 only) are extra 1x1 K-segments accumulated into the same
     output — used to fuse ResBlock.skip_connection(x) (openaimodel.py:240,274) into out_layers' conv."""
     NB, H, W, C = x.shape
-    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    # padding (1 - tap_off) on the top/left, 1 on the bottom/right: tap_off = 1 is F.pad(x, (0,1,0,1)) + padding 0
+    Ho, Wo = (H - 1 - tap_off) // stride + 1, (W - 1 - tap_off) // stride + 1
     N = w.shape[0]
     if out is None:
         out = torch.empty((NB, Ho, Wo, N), device=x.device, dtype=torch.float16)
@@ -255,7 +267,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
         segs.append((s, 1, s.shape[3], (s.stride(2), s.stride(1), s.stride(0))))
     gemm_raw(segs, in_w=W, in_h=H, stride=stride, W=Wo, H=Ho, NB=NB, w=w, N=N, K=w.stride(0), act=act,
              bias=bias, rowadd=rowadd, residual=residual, out=out,
-             so=(out.stride(0), 0, out.stride(1), out.stride(2), 0, 1))
+             so=(out.stride(0), 0, out.stride(1), out.stride(2), 0, 1), tap_off=tap_off)
     return out
 
 
@@ -371,7 +383,8 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     return out
 
 
-def nchw_to_nhwc(x: torch.Tensor, cpad: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def nchw_to_nhwc(x: torch.Tensor, cpad: Optional[int] = None, out: Optional[torch.Tensor] = None, *,
+                 mul: float = 1.0, add: float = 0.0) -> torch.Tensor:
     NB, C, H, W = x.shape
     cpad = cpad or C
     x = x.contiguous()
@@ -379,7 +392,7 @@ def nchw_to_nhwc(x: torch.Tensor, cpad: Optional[int] = None, out: Optional[torc
         out = torch.empty((NB, H, W, cpad), device=x.device, dtype=torch.float16)
     if x.dtype not in (torch.float16, torch.float32):
         raise RuntimeError(f"nchw_to_nhwc: unsupported dtype {x.dtype}")
-    _check(load().pfd_nchw_to_nhwc_f16(x.data_ptr(), int(x.dtype == torch.float32), NB, C, H, W, cpad,
+    _check(load().pfd_nchw_to_nhwc_f16(x.data_ptr(), int(x.dtype == torch.float32), NB, C, H, W, cpad, mul, add,
                                        out.data_ptr(), stream_ptr()), "pfd_nchw_to_nhwc_f16")
     return out
 
@@ -424,10 +437,62 @@ def add_rowvec(a: torch.Tensor, row: torch.Tensor, out: Optional[torch.Tensor] =
 
 
 def ddim_step(eps: torch.Tensor, x: torch.Tensor, guidance: float, coef: torch.Tensor,
-              step: Optional[torch.Tensor], x_prev: torch.Tensor, pred_x0: Optional[torch.Tensor]) -> None:
+              step: Optional[torch.Tensor], x_prev: torch.Tensor, pred_x0: Optional[torch.Tensor], *,
+              noise: Optional[torch.Tensor] = None, temperature: float = 1.0,
+              log_tab: Optional[torch.Tensor] = None, log_xt: Optional[torch.Tensor] = None,
+              log_x0: Optional[torch.Tensor] = None) -> None:
+    """Fused CFG combine + DDIM update (see pfd_ddim_step_f16); eps holds [uncond | cond] halves."""
     _check(load().pfd_ddim_step_f16(eps.data_ptr(), x.data_ptr(), x.numel(), guidance, coef.data_ptr(),
-                                    _p(step), x_prev.data_ptr(), _p(pred_x0), stream_ptr()),
+                                    _p(step), x_prev.data_ptr(), _p(pred_x0), _p(noise), float(temperature),
+                                    _p(log_tab), _p(log_xt), _p(log_x0), stream_ptr()),
            "pfd_ddim_step_f16")
+
+
+def ddim_begin_step(step: torch.Tensor, ttab: torch.Tensor, t_out: torch.Tensor) -> None:
+    """Device-side loop header: step -= 1; t_out[:] = ttab[step] (see pfd_ddim_begin_step)."""
+    if step.dtype != torch.int32 or ttab.dtype != torch.int64 or t_out.dtype != torch.int64:
+        raise RuntimeError("ddim_begin_step: step int32, ttab / t_out int64 expected")
+    _check(load().pfd_ddim_begin_step(step.data_ptr(), ttab.data_ptr(), t_out.data_ptr(), t_out.numel(),
+                                      stream_ptr()), "pfd_ddim_begin_step")
+
+
+def vae_posterior(moments: torch.Tensor, zc: int, *, noise: Optional[torch.Tensor] = None, scale: float = 1.0,
+                  want=("mean", "logvar", "std", "sample")):
+    """moments: channel-last [B,H,W,cpad] fp16 -> dict of NCHW fp16 [B,zc,H,W] tensors (pfd_vae_posterior_f16)."""
+    B, H, W, cpad = moments.shape
+    outs = {k: torch.empty((B, zc, H, W), device=moments.device, dtype=torch.float16) for k in want}
+    if noise is not None and (noise.dtype != torch.float32 or not noise.is_contiguous()):
+        noise = noise.to(torch.float32).contiguous()
+    _check(load().pfd_vae_posterior_f16(moments.data_ptr(), B, zc, H, W, cpad, _p(noise), scale,
+                                        _p(outs.get("mean")), _p(outs.get("logvar")), _p(outs.get("std")),
+                                        _p(outs.get("sample")), stream_ptr()), "pfd_vae_posterior_f16")
+    return outs
+
+
+def canny(x: torch.Tensor, low: int = 100, high: int = 200) -> Tuple[torch.Tensor, int]:
+    """NCHW [B,3,H,W] image in [0,1] (fp16/fp32) -> (float32 [B,3,H,W] edge map, hysteresis sweeps).  Bit-exact
+    cv2.Canny(ToPILImage(x), low, high) (pfd_canny_f32); synchronises the stream."""
+    if x.dim() != 4 or x.shape[1] != 3 or not x.is_cuda or x.dtype not in (torch.float16, torch.float32):
+        raise RuntimeError(f"canny: expected a CUDA fp16/fp32 [B,3,H,W] image, got {tuple(x.shape)} {x.dtype} {x.device}")
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    ws = torch.empty(int(load().pfd_canny_workspace_bytes(B, H, W)), device=x.device, dtype=torch.uint8)
+    out = torch.empty((B, 3, H, W), device=x.device, dtype=torch.float32)
+    sweeps = c_int32(0)
+    _check(load().pfd_canny_f32(x.data_ptr(), int(x.dtype == torch.float32), B, H, W, int(low), int(high),
+                                ws.data_ptr(), out.data_ptr(), ctypes.byref(sweeps), stream_ptr()), "pfd_canny_f32")
+    return out, int(sweeps.value)
+
+
+def image_u8_roundtrip(x: torch.Tensor) -> torch.Tensor:
+    """ToTensor(ToPILImage(x)) = floor(x*255)/255 as float32 (pfd_image_u8_roundtrip_f32)."""
+    if not x.is_cuda or x.dtype not in (torch.float16, torch.float32):
+        raise RuntimeError("image_u8_roundtrip: expected a CUDA fp16/fp32 tensor")
+    x = x.contiguous()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _check(load().pfd_image_u8_roundtrip_f32(x.data_ptr(), int(x.dtype == torch.float32), x.numel(), out.data_ptr(),
+                                             stream_ptr()), "pfd_image_u8_roundtrip_f32")
+    return out
 
 
 def window_gather(x: torch.Tensor, ws: int, shift: int) -> torch.Tensor:
@@ -476,18 +541,6 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, *, B: int, he
     _check(load().pfd_flash_attn_f16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, heads, Nq, Nk,
                                      d, q.shape[1], k.shape[1], scale, vt.shape[2], out.stride(0), out.stride(1),
                                      0, stream_ptr()), "pfd_flash_attn_f16")
-    return out
-
-
-def flash_attn_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, Nq: int, Nk: int, scale: float,
-                   out: torch.Tensor) -> torch.Tensor:
-    """Fused attention v2 (pfd_flash_attn_qkv_f16): q/k/v are strided views [B, heads, N(p), d] with d
-    contiguous (e.g. slices of one fused projection output); out [B, Nq, heads*d]."""
-    B, heads, _, d = q.shape
-    st = lambda t: (c_int64 * 3)(t.stride(0), t.stride(1), t.stride(2))
-    _check(load().pfd_flash_attn_qkv_f16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nk,
-                                         d, st(q), st(k), st(v), scale, out.stride(0), out.stride(1), stream_ptr()),
-           "pfd_flash_attn_qkv_f16")
     return out
 
 

@@ -103,13 +103,30 @@ class PromptFreeDiffusion(nn.Module):
 
     @torch.no_grad()
     def vae_encode(self, x, which, **kwargs):
-        raise NotImplementedError("VAE encode is outside the pfd_b200 hot path (SURVEY.md §8f)")
+        """pfd.py:266-273: AutoencoderKL.encode -> scale * z."""
+        scale = self.latent_scale_factor.get(which, None) if self.latent_scale_factor is not None else None
+        if kwargs.get("out_posterior", False):
+            return self.vae[which].encode(x, **kwargs)
+        return self.vae[which].encode(x, post_scale=1.0 if scale is None else float(scale), **kwargs)
+
+    @torch.no_grad()
+    def q_sample(self, x_start, t, noise=None):
+        """pfd.py:204-207: sqrt(acp[t]) * x0 + sqrt(1-acp[t]) * noise (per-sample timestep tensor t)."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        x0 = x_start.to(torch.float16).contiguous()
+        nz = noise.to(torch.float16).contiguous()
+        out = torch.empty_like(x0)
+        tl = [int(v) for v in t.reshape(-1).tolist()]
+        for i, ti in enumerate(tl):
+            nv.axpby(x0[i], float(self.sqrt_alphas_cumprod[ti]), nz[i], float(self.sqrt_one_minus_alphas_cumprod[ti]),
+                     out=out[i])
+        return out
 
     @torch.no_grad()
     def ctx_encode(self, x, which, **kwargs):
         """pfd.py:284-289."""
         if which.find("vae_") == 0:
-            raise NotImplementedError("vae_* context encoders are outside the pfd_b200 hot path")
+            return self.vae[which[4:]].encode(x, **kwargs)
         enc = self.ctx[which]
         if not (self.use_cuda_graphs and x.is_cuda) or kwargs:
             return enc.encode(x, **kwargs)
@@ -139,6 +156,20 @@ class PromptFreeDiffusion(nn.Module):
         gl = x_type if self.global_layer_ptr is None else self.global_layer_ptr
         assert gl == x_type == c_type, "pfd_b200 runs single-modality pipelines (image/image)"
         return self.diffuser[x_type].apply(x, timesteps, c, control=None, kv=kv)
+
+    @torch.no_grad()
+    def apply_model_multicontext(self, x_info, timesteps, c_info_list, mixing_type="attention"):
+        """pfd.py:367-439: every context block output is the ratio-weighted sum over the contexts
+        (`context_mixing`, 'attention' mixing; the stochastic 'layer' mixing is not used by the sampler)."""
+        if mixing_type != "attention":
+            raise NotImplementedError("only 'attention' context mixing is used (ddim.py:273,278)")
+        x_type, x = x_info["type"], x_info["x"]
+        ratios = np.array([float(c["ratio"]) for c in c_info_list], dtype=np.float64)
+        ratios = ratios / ratios.sum()
+        for c in c_info_list:
+            assert c["type"] == x_type, "pfd_b200 runs single-modality pipelines (image/image)"
+        ctxs = [(c["c"].to(torch.float16).contiguous(), float(r)) for c, r in zip(c_info_list, ratios)]
+        return self.diffuser[x_type].apply(x, timesteps, ctxs[0][0], mixed_contexts=ctxs)
 
     def get_device(self):
         return next(self.parameters()).device

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import native as nv
 from . import attention as att
-from .attention import attend, attend_qkv, ceil8, project_heads, project_heads_fused, project_vt_swapped
+from .attention import attend, ceil8, project_heads, project_heads_fused, project_vt_swapped
 from .modules import (Conv2d, GroupNorm, IndexedSequential, LayerNorm, Linear, cached, pk_conv3,
                       pk_conv3_small, pk_lin, pk_mat, pk_norm)
 
@@ -161,10 +161,6 @@ def context_kv(st: SpatialTransformer, context: torch.Tensor) -> Tuple[torch.Ten
     blk = st.transformer_blocks[0]
     Bc, Nk, Cc = context.shape
     ctx2d = context.reshape(Bc * Nk, Cc)
-    if att.USE_FLASH_V2:
-        wkv = _cat_weights(blk.attn2, "kv_cat", [blk.attn2.to_k, blk.attn2.to_v])
-        kv = project_heads_fused(ctx2d, wkv, None, Bc, Nk, st.n_heads, st.d_head, 2)
-        return kv[:, :st.n_heads], kv[:, st.n_heads:]
     wk, _ = pk_lin(blk.attn2.to_k)
     wv, _ = pk_lin(blk.attn2.to_v)
     k = project_heads(ctx2d, wk, None, Bc, Nk, st.n_heads, st.d_head)
@@ -187,10 +183,7 @@ def run_spatial_transformer(st: SpatialTransformer, x: torch.Tensor, context: to
     g, b = pk_norm(blk.norm1)
     n1 = nv.layernorm(t, g, b, blk.norm1.eps)
     a = blk.attn1
-    if att.USE_FLASH_V2:
-        qkv = project_heads_fused(n1, _cat_weights(a, "qkv_cat", [a.to_q, a.to_k, a.to_v]), None, B, N, heads, d, 3)
-        o = attend_qkv(qkv[:, :heads], qkv[:, heads:2 * heads], qkv[:, 2 * heads:], Nq=N, Nk=N, scale=a.scale)
-    elif att.USE_FUSED_QK and N % 8 == 0:
+    if att.USE_FUSED_QK and N % 8 == 0:
         qk = project_heads_fused(n1, _cat_weights(a, "qk_cat", [a.to_q, a.to_k]), None, B, N, heads, d, 2)
         vt4 = project_vt_swapped(n1, pk_lin(a.to_v)[0], B, N, heads, d)
         o = nv.flash_attn_strided(qk[:, :heads], qk[:, heads:], vt4, Nq=N, Nk=N, scale=a.scale,
@@ -208,12 +201,8 @@ def run_spatial_transformer(st: SpatialTransformer, x: torch.Tensor, context: to
     a = blk.attn2
     if kv is None:
         kv = context_kv(st, context)
-    if att.USE_FLASH_V2:
-        q = project_heads_fused(n2, pk_lin(a.to_q)[0], None, B, N, heads, d, 1)
-        o = attend_qkv(q, kv[0], kv[1], Nq=N, Nk=context.shape[1], scale=a.scale)
-    else:
-        q = project_heads(n2, pk_lin(a.to_q)[0], None, B, N, heads, d)
-        o = attend(q, kv[0], kv[1], B=B, heads=heads, Nq=N, Nk=context.shape[1], scale=a.scale)
+    q = project_heads(n2, pk_lin(a.to_q)[0], None, B, N, heads, d)
+    o = attend(q, kv[0], kv[1], B=B, heads=heads, Nq=N, Nk=context.shape[1], scale=a.scale)
     w, bb = pk_lin(a.to_out[0])
     t = nv.linear(o.reshape(B * N, inner), w, bb, residual=t)
     # --- GEGLU feed-forward (attention.py:305)
@@ -375,9 +364,12 @@ class UNetModel2D_Next(nn.Module):
 
     def apply(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
               control: Optional[List[torch.Tensor]] = None,
-              kv: Optional[List[Tuple[torch.Tensor, torch.Tensor]]] = None) -> torch.Tensor:
+              kv: Optional[List[Tuple[torch.Tensor, torch.Tensor]]] = None,
+              mixed_contexts: Optional[List[Tuple[torch.Tensor, float]]] = None) -> torch.Tensor:
         """pfd.py:314-365 / 466-528.  x: NCHW latents, context [B, Nk, Cctx], control: ControlNet
-        residuals as channel-last tensors (list of 13, consumed from the end).  Returns NCHW fp16."""
+        residuals as channel-last tensors (list of 13, consumed from the end).  Returns NCHW fp16.
+        mixed_contexts: [(context, ratio)] — pfd.py:367-439 `apply_model_multicontext` ('attention' mixing): every
+        context block becomes sum_i ratio_i * block(h, context_i)."""
         x = x.to(torch.float16)
         context = context.to(torch.float16).contiguous()
         B = x.shape[0]
@@ -386,7 +378,7 @@ class UNetModel2D_Next(nn.Module):
         rbs = [i for i, blk in enumerate(self.data_blocks) if isinstance(blk[0], ResBlock)]
         emb_list = batched_emb_layers(self, [self.data_blocks[i][0] for i in rbs], silu_emb)
         embs = dict(zip(rbs, emb_list))
-        if kv is None:
+        if kv is None and mixed_contexts is None:
             kv = self.prepare_context(context)
         ccs = list(control) if control is not None else None
         h = nv.nchw_to_nhwc(x)
@@ -399,7 +391,15 @@ class UNetModel2D_Next(nn.Module):
                 h2 = None
                 di += 1
             elif lt == 'c':
-                h = run_spatial_transformer(self.context_blocks[ci][0], h, context, kv[ci])
+                st = self.context_blocks[ci][0]
+                if mixed_contexts is None:
+                    h = run_spatial_transformer(st, h, context, kv[ci])
+                else:                                                    # pfd.py:374-379 context_mixing
+                    acc = None
+                    for cm, r in mixed_contexts:
+                        hi = run_spatial_transformer(st, h, cm.to(torch.float16).contiguous(), None)
+                        acc = nv.axpby(hi, r) if acc is None else nv.axpby(acc, 1.0, hi, r)
+                    h = acc
                 ci += 1
             elif lt == 'save_hidden_feature':
                 hs.append(h)

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = native.load()
     for name in _declared():
         assert hasattr(lib, name), f"{name} declared in include/pfd_b200.h but not exported"
-    assert lib.pfd_version() == 1
+    assert lib.pfd_version() == 2
 
 
 def test_python_binding_lists_match_header():

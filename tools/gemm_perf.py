@@ -62,13 +62,6 @@ def main():
             res.append(dict(op="attention" + ("_flash" if flash else "_unfused"), B=Bb, heads=heads, Nq=Nq, Nk=Nk, d=d, ms=ms,
                             tflops=4.0 * Bb * heads * Nq * Nk * d / ms / 1e9))
         att.USE_FLASH = True
-        # v2: strided [B, heads, N, d] operands, V in [keys, d] layout
-        q4 = q.reshape(Bb, heads, Nq, d)
-        k4 = k[:, :Nk].reshape(Bb, heads, Nk, d).contiguous()
-        v4 = vt[:, :, :Nk].transpose(1, 2).reshape(Bb, heads, Nk, d).contiguous()
-        ms = timeit(lambda: nv.flash_attn_qkv(q4, k4, v4, Nq=Nq, Nk=Nk, scale=d ** -0.5, out=o), n=5)
-        res.append(dict(op="attention_flash_v2", B=Bb, heads=heads, Nq=Nq, Nk=Nk, d=d, ms=ms,
-                        tflops=4.0 * Bb * heads * Nq * Nk * d / ms / 1e9))
     for r in res:
         print(json.dumps(r))
 
