@@ -251,8 +251,11 @@ def _data_block(sd, p, blk, h, emb):
 
 
 def unet_apply(sd: SD, cfg, x: torch.Tensor, t: torch.Tensor, context: torch.Tensor,
-               control: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
-    """pfd.py:314-365 / 466-528: walk i/m/o orders; `control` = ControlNet outputs (popped from the end)."""
+               control: Optional[List[torch.Tensor]] = None,
+               mixed: Optional[Sequence[Tuple[torch.Tensor, float]]] = None) -> torch.Tensor:
+    """pfd.py:314-365 / 466-528: walk i/m/o orders; `control` = ControlNet outputs (popped from the end).
+    mixed = [(context_i, ratio_i)]: pfd.py:367-439 apply_model_multicontext with 'attention' mixing - every context
+    block output is sum_i block(h, context_i) * (ratio_i / sum ratio) (pfd.py:374-379)."""
     data, ctxs, i_order, m_order, o_order = unet_plan(cfg)
     dtype = x.dtype
     t_emb = timestep_embedding(t, cfg["model_channels"]).to(dtype)      # pfd.py:486
@@ -269,7 +272,16 @@ def unet_apply(sd: SD, cfg, x: torch.Tensor, t: torch.Tensor, context: torch.Ten
             di += 1
         elif ltype == "c":
             c = ctxs[ci]
-            h = spatial_transformer(sd, f"context_blocks.{ci}.0.", h, context, c["heads"])
+            if mixed is None:
+                h = spatial_transformer(sd, f"context_blocks.{ci}.0.", h, context, c["heads"])
+            else:
+                rs = np.array([r for _, r in mixed], dtype=np.float64)
+                rs = rs / rs.sum()
+                acc = None
+                for (cm, _), r in zip(mixed, rs):
+                    hi = spatial_transformer(sd, f"context_blocks.{ci}.0.", h, cm, c["heads"]) * r
+                    acc = hi if acc is None else acc + hi
+                h = acc
             ci += 1
 
     for lt in i_order:
@@ -399,6 +411,35 @@ def vae_decode(sd: SD, cfg, z: torch.Tensor, scale_factor: Optional[float] = PFD
             h = _conv(h, sd, f"decoder.up.{lvl}.upsample.conv")
     h = _conv(F.silu(_gn(h, sd, "decoder.norm_out", 1e-6)), sd, "decoder.conv_out")
     return torch.clamp((h + 1) / 2, 0, 1)
+
+
+def vae_encode_moments(sd: SD, cfg, x: torch.Tensor):
+    """autokl.py:33-42 + Encoder.forward (autokl_modules.py:436-459) + Downsample (autokl_modules.py:69-76:
+    F.pad(x, (0,1,0,1)) then a stride-2 conv with padding 0) + DiagonalGaussianDistribution.__init__
+    (distributions.py:24-31).  x: [B,3,H,W] in [0,1]; returns (mean, logvar clamped to [-30, 20]); sd = 'vae.image.*'."""
+    h = _conv(x * 2 - 1, sd, "encoder.conv_in")
+    nlev = len(cfg["ch_mult"])
+    for lvl in range(nlev):
+        for bi in range(cfg["num_res_blocks"]):
+            h = vae_resnet(sd, f"encoder.down.{lvl}.block.{bi}.", h)
+        if lvl != nlev - 1:
+            h = _conv(F.pad(h, (0, 1, 0, 1), mode="constant", value=0), sd, f"encoder.down.{lvl}.downsample.conv",
+                      stride=2, padding=0)
+    h = vae_resnet(sd, "encoder.mid.block_1.", h)
+    h = vae_attn(sd, "encoder.mid.attn_1.", h)
+    h = vae_resnet(sd, "encoder.mid.block_2.", h)
+    h = _conv(F.silu(_gn(h, sd, "encoder.norm_out", 1e-6)), sd, "encoder.conv_out")
+    mean, logvar = torch.chunk(_conv(h, sd, "quant_conv", padding=0), 2, dim=1)
+    return mean, torch.clamp(logvar, -30.0, 20.0)
+
+
+def vae_encode(sd: SD, cfg, x: torch.Tensor, noise: torch.Tensor,
+               scale_factor: Optional[float] = PFD["latent_scale_factor"]) -> torch.Tensor:
+    """pfd.py:266-273: scale * (mean + exp(0.5*logvar) * noise) with the caller-supplied posterior noise
+    (the reference draws torch.randn(mean.shape) on the CPU, distributions.py:36)."""
+    mean, logvar = vae_encode_moments(sd, cfg, x)
+    z = mean + torch.exp(0.5 * logvar) * noise
+    return z * scale_factor if scale_factor is not None else z
 
 
 # ---------------------------------------------------------------------------------------------
@@ -618,15 +659,17 @@ def seecoder_encode(sd: SD, img: torch.Tensor, swin_cfg=SWIN_L, dec_cfg=SEECODER
 # ---------------------------------------------------------------------------------------------
 # DDIM sampler (ddim.py:58-172)
 # ---------------------------------------------------------------------------------------------
-def ddim_update(x, e_t, a_t, a_prev, sigma_t, sqrt_one_minus_at):
-    """ddim.py:159-171 with eta=0 noise term dropped (sigma_t * noise == 0); coefficients are
-    torch.full(..., dtype=x.dtype) tensors exactly as in the reference."""
+def ddim_update(x, e_t, a_t, a_prev, sigma_t, sqrt_one_minus_at, noise=None, temperature=1.0):
+    """ddim.py:159-171; coefficients are torch.full(..., dtype=x.dtype) tensors exactly as in the reference.
+    noise=None: the eta = 0 case (sigma_t * noise == 0)."""
     b = x.shape[0]
     ext = [b] + [1] * (x.dim() - 1)
     mk = lambda v: torch.full(ext, float(v), dtype=x.dtype, device=x.device)
     a_t, a_prev, sigma_t, s1m = mk(a_t), mk(a_prev), mk(sigma_t), mk(sqrt_one_minus_at)
     pred_x0 = (x - s1m * e_t) / a_t.sqrt()
     dir_xt = (1.0 - a_prev - sigma_t ** 2).sqrt() * e_t
+    if noise is not None:
+        return a_prev.sqrt() * pred_x0 + dir_xt + sigma_t * noise * temperature, pred_x0
     return a_prev.sqrt() * pred_x0 + dir_xt, pred_x0
 
 
@@ -634,11 +677,15 @@ def ddim_sample(unet_sd: SD, unet_cfg, alphas_cumprod: torch.Tensor, *, steps: i
                 cond: torch.Tensor, uncond: Optional[torch.Tensor], guidance: float,
                 ctl_sd: Optional[SD] = None, ctl_cfg=None, hint: Optional[torch.Tensor] = None,
                 trace: Optional[list] = None, max_evals: Optional[int] = None,
-                n_forward: Optional[int] = None) -> torch.Tensor:
-    """ddim.py:81-172 with eta = 0 and x_T supplied (the reference draws it with torch.randn, :105).
+                n_forward: Optional[int] = None, eta: float = 0.0, noises: Optional[Sequence[torch.Tensor]] = None,
+                temperature: float = 1.0, mixed: Optional[Sequence[Tuple[torch.Tensor, Optional[torch.Tensor], float]]] = None
+                ) -> torch.Tensor:
+    """ddim.py:81-172 with x_T supplied (the reference draws it with torch.randn, :105).
     n_forward: the img2img branch (ddim.py:94-101) - x_T is x0 already noised to timestep ts[n_forward] and only
-    the first n_forward timesteps are walked."""
-    ts, alphas, alphas_prev, sigmas, s1m = ddim_schedule(alphas_cumprod, steps, 0.0)
+    the first n_forward timesteps are walked.  eta > 0: `noises[i]` is the noise_like() draw of step i
+    (ddim.py:168).  mixed = [(cond_i, uncond_i, ratio_i)]: sample_multicontext (ddim.py:174-299); `cond` /
+    `uncond` are then ignored."""
+    ts, alphas, alphas_prev, sigmas, s1m = ddim_schedule(alphas_cumprod, steps, eta)
     if n_forward is not None:
         ts = ts[:n_forward]
     x = x_T
@@ -649,7 +696,15 @@ def ddim_sample(unet_sd: SD, unet_cfg, alphas_cumprod: torch.Tensor, *, steps: i
             break
         index = total - i - 1
         t = torch.full((b,), int(step), dtype=torch.long, device=x.device)
-        if guidance == 1.0 or uncond is None:
+        if mixed is not None:
+            if guidance == 1.0:
+                e_t = unet_apply(unet_sd, unet_cfg, x, t, None, mixed=[(c, r) for c, _, r in mixed])
+            else:
+                x_in, t_in = torch.cat([x] * 2), torch.cat([t] * 2)
+                e_u, e_c = unet_apply(unet_sd, unet_cfg, x_in, t_in, None,
+                                      mixed=[(torch.cat([u, c]), r) for c, u, r in mixed]).chunk(2)
+                e_t = e_u + guidance * (e_c - e_u)
+        elif guidance == 1.0 or uncond is None:
             control = controlnet_apply(ctl_sd, ctl_cfg, x, hint, t, cond) if hint is not None else None
             e_t = unet_apply(unet_sd, unet_cfg, x, t, cond, control) * guidance
         else:
@@ -660,5 +715,6 @@ def ddim_sample(unet_sd: SD, unet_cfg, alphas_cumprod: torch.Tensor, *, steps: i
             e_t = e_u + guidance * (e_c - e_u)
         if trace is not None:
             trace.append(dict(x=x.clone(), e_t=e_t.clone(), t=int(step)))
-        x, _ = ddim_update(x, e_t, alphas[index], alphas_prev[index], sigmas[index], s1m[index])
+        nz = noises[i] if (noises is not None and eta != 0.0) else None
+        x, _ = ddim_update(x, e_t, alphas[index], alphas_prev[index], sigmas[index], s1m[index], nz, temperature)
     return x

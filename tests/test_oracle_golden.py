@@ -142,3 +142,54 @@ def test_swin_mask_and_index_builders_agree_with_product():
     assert torch.equal(relative_position_index(12), O.relative_position_index(12))
     for (H, W) in [(32, 32), (16, 20), (8, 8)]:
         assert torch.equal(shift_mask(H, W, 12, 6), O.swin_shift_mask(H, W, 12, 6, torch.float32))
+
+
+# ---- round 2: the oracle's eta / VAE-encode / multicontext restatements against the reference's outputs at the
+#      config fixtures (tests/golden/config_outputs.npz, tools/make_golden_configs.py); the cheap cases run here,
+#      the full-size ones (64x64 / 96x96 latents) are compared with the CUDA path in tests/test_configs_gpu.py.
+@pytest.fixture(scope="module")
+def cgold():
+    return dict(np.load(os.path.join(GOLD, "config_outputs.npz")))
+
+
+def test_oracle_eta_sampler_matches_reference(shapes, cgold):
+    from oracle.golden_inputs import config_inputs
+    inp = config_inputs()
+    usd = _sd(shapes, "diffuser.image.")
+    with torch.no_grad():
+        x = O.ddim_sample(usd, O.UNET_SD15, O.schedule_buffers()["alphas_cumprod"], steps=4, x_T=inp["c7_xT"],
+                          cond=inp["c7_cond"], uncond=torch.zeros_like(inp["c7_cond"]), guidance=2.0, eta=0.5,
+                          noises=inp["c7_noise"])
+    _close(x, cgold["c7_latent"])
+
+
+def test_oracle_vae_encode_matches_reference(shapes, cgold):
+    from oracle.golden_inputs import config_inputs
+    inp = config_inputs()
+    with torch.no_grad():
+        mean, logvar = O.vae_encode_moments(_sd(shapes, "vae.image."), O.VAE_SD, inp["c8_img"])
+    _close(mean, cgold["c8_mean"])
+    _close(logvar, cgold["c8_logvar"])
+    nz = torch.randn(mean.shape, generator=torch.Generator().manual_seed(0))
+    z = O.vae_encode(_sd(shapes, "vae.image."), O.VAE_SD, inp["c8_img"], nz)
+    assert torch.allclose(z, 0.18215 * (mean + torch.exp(0.5 * logvar) * nz), atol=1e-6)
+
+
+def test_oracle_multicontext_matches_reference(shapes, cgold):
+    from oracle.golden_inputs import config_inputs
+    inp = config_inputs()
+    usd = _sd(shapes, "diffuser.image.")
+    ca, cb = inp["c9_cond_a"], inp["c9_cond_b"]
+    with torch.no_grad():
+        x = O.ddim_sample(usd, O.UNET_SD15, O.schedule_buffers()["alphas_cumprod"], steps=4, x_T=inp["c9_xT"],
+                          cond=None, uncond=None, guidance=2.0,
+                          mixed=[(ca, torch.zeros_like(ca), 0.3), (cb, torch.zeros_like(cb), 0.7)])
+    _close(x, cgold["c9_latent"])
+
+
+def test_config_fixture_is_complete(cgold):
+    need = ["c1_ctx", "c1_latent", "c1_image", "c2_eps_t981", "c2_eps_t501", "c2_eps_t1", "c3_eps", "c4_eps",
+            "c5_ctx", "c5_x_step0", "c5_x_step1", "c6_ctx", "c7_latent", "c8_mean", "c8_logvar", "c9_latent"]
+    assert all(k in cgold for k in need), [k for k in need if k not in cgold]
+    assert cgold["c2_eps_t501"].shape == (8, 4, 64, 64) and cgold["c5_x_step1"].shape == (1, 4, 96, 96)
+    assert cgold["c1_image"].shape == (1, 3, 512, 512)

@@ -1,14 +1,30 @@
-"""Import harness for the UNMODIFIED reference (SHI-Labs/Prompt-Free-Diffusion at /root/reference).
+"""Import harness for the UNMODIFIED reference (SHI-Labs/Prompt-Free-Diffusion).
 
-Only usable in the build container (the reference tree does not travel to the GPU box); used by
-tools/make_golden.py and tools/validate_oracle.py to pin the oracle.  Recipe: SURVEY.md App. D.
-Nothing here is imported by the product or by the tests.
+The reference tree is /root/reference in the build container and its verbatim staged copy baseline/_ref on
+the GPU box (tools/install_reference.py; git-ignored, shipped by gpurun).  Used by tools/make_golden*.py to pin
+the oracle / write the golden fixtures, by bench.py's reference arms (the reference's own modules timed on the
+host CPU and in eager fp16 on the same GPU) and by the optional reference-side parity tests.  Recipe: SURVEY.md
+App. D.  Nothing here is imported by the product.
 """
 import os
 import sys
 import types
 
-REF = os.environ.get("PFD_REFERENCE", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    for cand in (os.environ.get("PFD_REFERENCE"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "lib", "model_zoo")):
+            return cand
+    return None
+
+
+REF = _find_reference()
+
+
+def available() -> bool:
+    return REF is not None
 
 
 class EasyDict(dict):
@@ -74,6 +90,8 @@ _imported = False
 def import_reference():
     """chdir into the reference tree (cfg_helper resolves 'configs/model' relative to CWD) and import."""
     global _imported
+    if REF is None:
+        raise RuntimeError("reference tree not found (neither /root/reference nor baseline/_ref)")
     install_shims()
     if not _imported:
         os.chdir(REF)
@@ -84,8 +102,11 @@ def import_reference():
     return model_cfg_bank, get_model
 
 
-def build_reference_net(name="pfd_seecoder_with_controlnet", overrides=None):
-    """Build the reference pipeline (random init).  `overrides(cfgm)` may shrink the config."""
+def build_reference_net(name="pfd_seecoder_with_controlnet", overrides=None, device=None):
+    """Build the reference pipeline (random init).  `overrides(cfgm)` may shrink the config.  device: construct
+    the parameters directly on that device (torch.device context) - random init of 1.6 B parameters takes ~50 s on
+    8 CPU cores and milliseconds on the GPU."""
+    import contextlib
     import torch
     model_cfg_bank, get_model = import_reference()
     cfgm = model_cfg_bank()(name)
@@ -93,9 +114,21 @@ def build_reference_net(name="pfd_seecoder_with_controlnet", overrides=None):
     if overrides is not None:
         overrides(cfgm)
     torch.manual_seed(0)
-    net = get_model()(cfgm)
+    ctx = torch.device(device) if device is not None else contextlib.nullcontext()
+    with ctx:
+        net = get_model()(cfgm)
     net.eval()
     return net, cfgm
+
+
+def fill_reference_net(net, seed=0):
+    """Load the name-seeded synthetic weights (pfd_b200/weights.py) into a reference net, on whatever device its
+    parameters live (values are generated on the CPU, so they are identical everywhere)."""
+    if _ROOT not in sys.path:
+        sys.path.insert(0, _ROOT)
+    from pfd_b200.weights import SCHEDULE_BUFFERS, fill_module_
+    fill_module_(net, seed=seed, skip=SCHEDULE_BUFFERS)
+    return net
 
 
 def cpu_sampler(net):
