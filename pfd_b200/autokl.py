@@ -114,18 +114,21 @@ class Decoder(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
+VAE_GN_UNIT = 4          # ch = 128: GroupNorm(32) groups of 4 / 8 / 16 channels are whole numbers of 4-channel units
+
+
 def run_vae_resnet(rb: ResnetBlock, x: torch.Tensor) -> torch.Tensor:
     g, b = pk_norm(rb.norm1)
     h = nv.groupnorm(x, g, b, rb.norm1.eps, silu=True)
     w, bb = pk_conv3(rb.conv1)
-    h = nv.conv3x3(h, w, bb)
+    h = nv.conv3x3(h, w, bb, stats_unit=VAE_GN_UNIT)
     g, b = pk_norm(rb.norm2)
     h = nv.groupnorm(h, g, b, rb.norm2.eps, silu=True)
     if rb.in_channels != rb.out_channels:
         w, bb = pk_conv3(rb.conv2, rb.nin_shortcut)
-        return nv.conv3x3(h, w, bb, skip=[x])
+        return nv.conv3x3(h, w, bb, skip=[x], stats_unit=VAE_GN_UNIT)
     w, bb = pk_conv3(rb.conv2)
-    return nv.conv3x3(h, w, bb, residual=x)
+    return nv.conv3x3(h, w, bb, residual=x, stats_unit=VAE_GN_UNIT)
 
 
 def run_vae_attn(at: AttnBlock, x: torch.Tensor) -> torch.Tensor:
@@ -143,13 +146,19 @@ def run_vae_attn(at: AttnBlock, x: torch.Tensor) -> torch.Tensor:
     vt = torch.empty((B, C, N), device=x.device, dtype=torch.float16)
     nv.gemm_raw([(hn, 1, C, (C, C * N, C * N))], in_w=N, in_h=1, stride=1, W=N, H=1, NB=B, w=wv, N=C, K=C,
                 bias=bv, out=vt, so=(C * N, 0, 0, 1, 0, N))
-    s = torch.empty((B, N, N), device=x.device, dtype=torch.float16)
-    nv.bmm_nt(q, k, out=s, so=(N * N, 0, 0, N, 0, 1))
-    nv.softmax_(s, float(C) ** -0.5)
+    # query rows are processed in chunks so the materialised fp16 scores stay <= ~512 MB (N = 36864 at 1536x1536
+    # would otherwise need 2.7 GB per image inside every cached graph's memory pool)
+    tq = max(128, min(N, ((1 << 28) // (B * N)) // 128 * 128))
     o = torch.empty((B, N, C), device=x.device, dtype=torch.float16)
-    nv.bmm_nt(s, vt, out=o, so=(N * C, 0, 0, C, 0, 1))
+    for r0 in range(0, N, tq):
+        rows = min(tq, N - r0)
+        sc = torch.empty((B, rows, N), device=x.device, dtype=torch.float16)
+        nv.bmm_nt(q[:, r0:r0 + rows], k, out=sc, so=(rows * N, 0, 0, N, 0, 1))
+        nv.softmax_(sc, float(C) ** -0.5)
+        nv.bmm_nt(sc, vt, out=o[:, r0:r0 + rows], so=(N * C, 0, 0, C, 0, 1))
     w, bb = pk_lin(at.proj_out)
-    return nv.linear(o.reshape(B * N, C), w, bb, residual=x.reshape(B * N, C)).reshape(B, H, W, C)
+    o2 = nv.linear(o.reshape(B * N, C), w, bb, residual=x.reshape(B * N, C), stats_unit=VAE_GN_UNIT)
+    return nv.carry_stats(o2.reshape(B, H, W, C), o2)
 
 
 class AutoencoderKL(nn.Module):
@@ -184,7 +193,7 @@ class AutoencoderKL(nn.Module):
                 h = run_vae_resnet(rb, h)
             if lvl != enc.num_resolutions - 1:
                 w, b = pk_conv3(enc.down[lvl].downsample.conv)
-                h = nv.conv3x3(h, w, b, stride=2, tap_off=1)
+                h = nv.conv3x3(h, w, b, stride=2, tap_off=1, stats_unit=VAE_GN_UNIT)
         h = run_vae_resnet(enc.mid.block_1, h)
         h = run_vae_attn(enc.mid.attn_1, h)
         h = run_vae_resnet(enc.mid.block_2, h)
@@ -222,7 +231,7 @@ class AutoencoderKL(nn.Module):
                 h = run_vae_resnet(rb, h)
             if lvl != 0:
                 w, b = pk_conv3(up.upsample.conv)
-                h = nv.conv3x3(nv.upsample2x(h), w, b)
+                h = nv.conv3x3(nv.upsample2x(h), w, b, stats_unit=VAE_GN_UNIT)
         g, b = pk_norm(dec.norm_out)
         h = nv.groupnorm(h, g, b, dec.norm_out.eps, silu=True)
         w, b = pk_conv3(dec.conv_out)                                      # rows padded 3 -> 8

@@ -25,13 +25,14 @@ namespace pfd {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+// threads = TMA warp + MMA warp + EW epilogue warps (EW = 8: 320 threads, up to 168 registers; EW = 16: 576 threads,
+// 112 registers - for the launches whose epilogue, not the MMA, bounds the tile time: small-K Linears, GEGLU)
+constexpr int gemm_threads(int ew) { return 64 + 32 * ew; }
 constexpr int STAGE_A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int SMEM_BUDGET = 232448;         // 227 KiB opt-in limit per CTA
-constexpr int EPI_WARPS = 8;
 constexpr int EPI_STG_BYTES = 1024;         // per epilogue warp: 16 rows x 64 B transpose buffer
 // alignment slack + barriers + epilogue transpose buffers + fp32 bias of the tile (double-buffered)
-constexpr int smem_fixed(int bn) { return 1024 + 256 + EPI_WARPS * EPI_STG_BYTES + 2 * bn * 4; }
+constexpr int smem_fixed(int bn, int ew) { return 1024 + 256 + ew * EPI_STG_BYTES + 2 * bn * 4; }
 
 struct alignas(64) GemmParams {
   CUtensorMap tmA[PFD_MAX_SEG];
@@ -47,7 +48,6 @@ struct alignas(64) GemmParams {
   int W, H, NB, N;
   int b_batched;
   int num_kb;
-  int b_resident;    // 1: this CTA's B tile (all K) stays in shared memory for all of its tiles
   int splits;        // split-K factor (1 = off); work items = tiles * splits
   int kb_per_split;
   float* ws;         // fp32 partials [splits][m_tiles*128][N] when splits > 1
@@ -61,15 +61,17 @@ struct alignas(64) GemmParams {
   long long rowadd_ld;
   int ndiv, cdiv;
   int vec_ok;
+  float* stats;      // optional [NB][N / stats_unit][2] fp32 (sum, sum of squares) of the final fp16 outputs
+  int stats_unit;    // channels per statistics unit (GroupNorm statistics from the producer epilogue)
 };
 
-template <int BN>
+template <int BN, int EW>
 struct GemmCfg {
   static constexpr int STAGE_B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-  static constexpr int RAW_STAGES = (SMEM_BUDGET - smem_fixed(BN)) / STAGE_BYTES;
+  static constexpr int RAW_STAGES = (SMEM_BUDGET - smem_fixed(BN, EW)) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + smem_fixed(BN);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + smem_fixed(BN, EW);
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128u : (2 * BN <= 256 ? 256u : 512u);
   static_assert(STAGE_B_BYTES % 1024 == 0, "B stage must keep 1024-B swizzle alignment");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
@@ -161,30 +163,27 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 // LEAN = true: epilogue for 16-byte-vectorisable outputs (channel-last rows, optional head split) without split-K;
 // LEAN = false keeps the general path (element-strided outputs such as V^T, split-K partials).
-template <int BN, bool LEAN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool LEAN, int EW>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
+  constexpr int EPI_WARPS = EW;
+  constexpr int NPART = EW / 4;             // epilogue warps per TMEM lane quarter (each takes a share of the columns)
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
-  // B-resident mode (small-K GEMMs, which are L2->SM traffic bound): the whole [BN x K] weight tile of this
-  // CTA's fixed n_tile is loaded once; the ring then stages A only (up to STAGES stages of 16 KB).
-  const int nkb_res = p.b_resident ? p.num_kb : 0;
   const uint32_t smemA = base;
-  const uint32_t smemB = base + STAGES * STAGE_A_BYTES;               // streaming mode: [STAGES][B tile]
-  const int nst = nkb_res > 0 ? 4 : STAGES;                           // A-ring depth
-  const uint32_t smemBres = base + 4 * STAGE_A_BYTES;                 // resident mode: [num_kb][B tile] after 4 A stages
+  const uint32_t smemB = base + STAGES * STAGE_A_BYTES;               // [STAGES][B tile]
+  constexpr int nst = STAGES;
   const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;
   // barrier layout: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t bres_bar = bars + 8u * (2 * STAGES + 5);
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_g =
       reinterpret_cast<volatile uint32_t*>(gbase + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
@@ -203,9 +202,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 256);
+      mbar_init(tempty_bar(a), 32 * EW);
     }
-    mbar_init(bres_bar, 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -228,13 +226,6 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (nkb_res > 0 && (int)blockIdx.x < total_work) {
-        // gridDim.x is a multiple of n_tiles -> every tile of this CTA has n_tile == blockIdx.x % n_tiles
-        const int n_tile_fixed = blockIdx.x % p.n_tiles;
-        mbar_expect_tx(bres_bar, (uint32_t)nkb_res * Cfg::STAGE_B_BYTES);
-        for (int kb = 0; kb < nkb_res; ++kb)
-          tma_load_3d(smemBres + kb * Cfg::STAGE_B_BYTES, &p.tmB, bres_bar, kb * BK, n_tile_fixed * BN, 0);
-      }
       for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
         const int tile = work % total_tiles;
         const int split = work / total_tiles;
@@ -259,12 +250,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < p.chunks[s]; ++j, ++kbi) {
               if (kbi < kb_begin || kbi >= kb_end) continue;
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_expect_tx(full_bar(stage), nkb_res > 0 ? STAGE_A_BYTES : Cfg::STAGE_BYTES);
+              mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
               tma_load_4d(smemA + stage * STAGE_A_BYTES, &p.tmA[s], full_bar(stage), j * BK,
                           x0 + dx, y0 + dy, n0);
-              if (nkb_res == 0)
-                tma_load_3d(smemB + stage * Cfg::STAGE_B_BYTES, &p.tmB, full_bar(stage),
-                            kofs + j * BK, n_tile * BN, bcoord);
+              tma_load_3d(smemB + stage * Cfg::STAGE_B_BYTES, &p.tmB, full_bar(stage),
+                          kofs + j * BK, n_tile * BN, bcoord);
               if (++stage == nst) {
                 stage = 0;
                 phase ^= 1u;
@@ -282,7 +272,6 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      if (nkb_res > 0 && (int)blockIdx.x < total_work) mbar_wait(bres_bar, 0);
       for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
@@ -295,8 +284,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint64_t adesc = make_sw128_kmajor_desc(smemA + stage * STAGE_A_BYTES);
-          const uint64_t bdesc = make_sw128_kmajor_desc(nkb_res > 0 ? smemBres + kb * Cfg::STAGE_B_BYTES
-                                                                    : smemB + stage * Cfg::STAGE_B_BYTES);
+          const uint64_t bdesc = make_sw128_kmajor_desc(smemB + stage * Cfg::STAGE_B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 fp16 = 32 B inside the 128-B swizzle atom: +2 in the (addr>>4) field
@@ -318,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     // 16 columns).  Per chunk all global loads (bias / row add / residual) are issued before the
     // TMEM load is waited on, index arithmetic is hoisted out of the chunk loop.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half_id = (warp - 2) >> 2;    // 0: warps 2..5, 1: warps 6..9
+    const int half_id = (warp - 2) >> 2;    // column share of this warp: 0 .. NPART-1
     const int row = q * 32 + lane;
     const int rdx = row % p.bw;
     const int rdy = (row / p.bw) % p.bh;
@@ -328,8 +316,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     constexpr int CB = BN;                  // accumulator columns per tile in TMEM
     const int ocols = geglu ? CB / 2 : CB;  // output columns this tile produces
     const int nch = ocols / 16;
-    const int ch_begin = half_id == 0 ? 0 : (nch + 1) / 2;
-    const int ch_end = half_id == 0 ? (nch + 1) / 2 : nch;
+    const int ch_begin = (nch * half_id + NPART - 1) / NPART;
+    const int ch_end = (nch * (half_id + 1) + NPART - 1) / NPART;
     const bool plain_cols = p.cdiv >= p.N;  // no head split: column offset = col * so_c0
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
@@ -419,7 +407,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         };
         if (geglu) {
           // ------ GEGLU: out[:, col] = value * gelu(gate), runs of 16 output columns (value + gate accumulators)
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
           mbar_wait(tfull_bar(as), aph);
           tc_fence_after();
           const uint32_t wr16 = stg + lane * 32;
@@ -463,11 +451,65 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           mbar_arrive(tempty_bar(as));
           continue;
         }
+        // GroupNorm statistics of the tile's FINAL fp16 values (after bias / row add / activation / residual), per
+        // (image, unit of `stats_unit` channels): accumulated per lane over the rows it stores, folded into the (at
+        // most two) units its 8 columns touch, reduced over the lanes that hold the same columns and added to the
+        // fp32 workspace with one atomic pair per unit per warp and run.  All 32 rows of a warp belong to one image
+        // (the host enables this only when bw * bh >= 32).
+        const bool do_stats = (EW == 8) && p.stats != nullptr;
+        const int st_unit = p.stats_unit > 0 ? p.stats_unit : 8;
+        const int st_n = tn * p.bn + (q * 32) / (p.bw * p.bh);
+        float ssum[8], ssq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = 0.f;
+        auto stats_add = [&](const uint4& o) {
+          const __half2* hh = reinterpret_cast<const __half2*>(&o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(hh[i]);
+            ssum[2 * i] += f.x;
+            ssum[2 * i + 1] += f.y;
+            ssq[2 * i] = fmaf(f.x, f.x, ssq[2 * i]);
+            ssq[2 * i + 1] = fmaf(f.y, f.y, ssq[2 * i + 1]);
+          }
+        };
+        // lanes_per_row = 4 (32-column runs) or 2 (16-column run); c = first of this lane's 8 output columns
+        auto stats_flush = [&](int c, int lanes_per_row, bool colok) {
+          const int u0 = c / st_unit;
+          const int sp = min(8, (u0 + 1) * st_unit - c);
+          float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < sp) {
+              a0 += ssum[i];
+              q0 += ssq[i];
+            } else {
+              a1 += ssum[i];
+              q1 += ssq[i];
+            }
+            ssum[i] = ssq[i] = 0.f;
+          }
+          for (int off = lanes_per_row; off < 32; off <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, off);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, off);
+          }
+          if (lane < lanes_per_row && colok && st_n < p.NB) {
+            float* sp0 = p.stats + ((long long)st_n * (n_lim / st_unit) + u0) * 2;
+            atomicAdd(sp0, a0);
+            atomicAdd(sp0 + 1, q0);
+            if (sp < 8 && c + sp < n_lim) {
+              atomicAdd(sp0 + 2, a1);
+              atomicAdd(sp0 + 3, q1);
+            }
+          }
+        };
         uint4 ra[4], rb[4];
         int c0 = cbeg;
         if (n32 > 0) load_res32(c0, ra);
         else if (tail16) load_res16(c0, ra);
-        asm volatile("bar.sync 1, 256;" ::: "memory");            // bias of this tile visible to all epilogue warps
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");   // bias of this tile visible to all epilogue warps
         mbar_wait(tfull_bar(as), aph);
         tc_fence_after();
         const uint32_t wr32 = stg + (lane & 15) * 64;
@@ -536,9 +578,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
                 uint4 o = ld_shared_v4(rd32 + it * 512);
                 if (has_res) o = hadd2x4(o, ra[j]);
                 *reinterpret_cast<uint4*>(p.out + roff4[j] + co) = o;
+                if constexpr (EW == 8) {
+                  if (do_stats) stats_add(o);
+                }
               }
             }
             __syncwarp();
+          }
+          if constexpr (EW == 8) {
+            if (do_stats) stats_flush(c, 4, colok);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) ra[j] = rb[j];
@@ -590,8 +638,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
                 uint4 o = ld_shared_v4(stg + rr * 32 + ((cc2 ^ ((rr >> 2) & 1)) << 4));
                 if (has_res) o = hadd2x4(o, ra[it]);
                 *reinterpret_cast<uint4*>(p.out + roff2[it] + co) = o;
+                if constexpr (EW == 8) {
+                  if (do_stats) stats_add(o);
+                }
               }
             }
+          }
+          if constexpr (EW == 8) {
+            if (do_stats) stats_flush(c, 2, c < n_lim);
           }
           __syncwarp();
         }
@@ -915,15 +969,6 @@ splitk_finish_kernel(const __grid_constant__ GemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------ host
-static inline bool gemm_bres_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PFD_BRES");      // opt-in: measured neutral-to-slower (r1 linperf / ksweep2 logs)
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
 constexpr size_t SPLITK_WS_BYTES = 64ull << 20;
 // One fp32 split-K workspace per DEVICE, allocated by the first pfd_gemm_f16 call on that device that is not
 // inside a stream capture (cudaMalloc is illegal while capturing) - i.e. in the eager warm-up pass that every
@@ -996,17 +1041,17 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
 
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
-template <int BN, bool LEAN>
+template <int BN, bool LEAN, int EW>
 static int launch_gemm_t(const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN, EW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_done = true;
   }
-  launch_k(gemm_tc_kernel<BN, LEAN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
+  launch_k(gemm_tc_kernel<BN, LEAN, EW>, dim3(grid), dim3(gemm_threads(EW)), Cfg::SMEM_BYTES, stream, p);
   return check_launch("pfd_gemm_f16");
 }
 
@@ -1019,9 +1064,17 @@ static inline bool gemm_lean_enabled() {
   return v == 1;
 }
 
+thread_local int g_last_stats = 0;
+
 template <int BN>
-static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream) {
   const bool lean = gemm_lean_enabled() && p.vec_ok && p.splits == 1;
+  // producer-side GroupNorm statistics: lean 8-warp epilogue only, plain channel-last output columns, every warp's
+  // 32 rows inside one image, at most two units per 8-column vector
+  const bool stats_ok = lean && p.stats != nullptr && p.act != PFD_ACT_GEGLU && p.cdiv >= p.N && p.bw * p.bh >= 32 &&
+                        (p.stats_unit == 4 || p.stats_unit >= 8) && p.N % p.stats_unit == 0;
+  if (!stats_ok) p.stats = nullptr;
+  g_last_stats = stats_ok ? 1 : 0;
   static int trace = -1;
   if (trace < 0) {
     const char* e = getenv("PFD_GEMM_TRACE");
@@ -1032,12 +1085,25 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
             "splits=%d grid=%d batched=%d vec=%d plain=%d\n", (long long)p.W * p.H * p.NB, p.N, p.num_kb * BK, p.nseg,
             p.taps[0], p.stride, p.act, p.bias != nullptr, p.residual != nullptr, p.rowadd != nullptr, BN, (int)lean,
             p.splits, grid, p.b_batched, p.vec_ok, (int)(p.cdiv >= p.N));
-  return lean ? launch_gemm_t<BN, true>(p, grid, stream) : launch_gemm_t<BN, false>(p, grid, stream);
+  if (!lean) return launch_gemm_t<BN, false, 8>(p, grid, stream);
+  // 16 epilogue warps where the epilogue bounds the tile: per 128 x BN tile the MMA takes ~num_kb * 2 * BN cycles,
+  // the 8-warp epilogue ~3400 (plain) to ~5000 (GEGLU) cycles (r1 ncu source-page measurements)
+  static int ew_mode = -1;      // PFD_GEMM_EW: 8 / 16 force the variant, anything else = automatic
+  if (ew_mode < 0) {
+    const char* e = getenv("PFD_GEMM_EW");
+    ew_mode = e ? atoi(e) : 0;
+  }
+  const long long mma_cycles = (long long)p.num_kb * 2 * BN;
+  const long long epi_cycles = p.act == PFD_ACT_GEGLU ? 5200 : 3400;
+  const bool wide = !stats_ok && (ew_mode == 16 || (ew_mode != 8 && mma_cycles < epi_cycles * 3 / 2));
+  return wide ? launch_gemm_t<BN, true, 16>(p, grid, stream) : launch_gemm_t<BN, true, 8>(p, grid, stream);
 }
 
 }  // namespace pfd
 
 using namespace pfd;
+
+extern "C" PFD_API int pfd_gemm_stats_written(void) { return g_last_stats; }
 
 extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   if (!d) return set_error("pfd_gemm_f16: null descriptor");
@@ -1079,6 +1145,11 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   p.so_c1 = d->so_c1; p.so_c0 = d->so_c0;
   p.ndiv = d->ndiv > 0 ? d->ndiv : 1;
   p.cdiv = d->cdiv > 0 ? d->cdiv : (1 << 30);
+  p.stats = static_cast<float*>(d->stats_out);
+  p.stats_unit = d->stats_unit;
+  if (p.stats && ((reinterpret_cast<uintptr_t>(p.stats) & 7) || d->stats_unit <= 0))
+    return set_error("pfd_gemm_f16: stats_out must be 8-byte aligned with stats_unit > 0");
+  g_last_stats = 0;
   p.vec_ok = (d->so_c0 == 1) && (p.cdiv % 8 == 0) && (d->so_n1 % 8 == 0) && (d->so_n0 % 8 == 0) &&
              (d->so_y % 8 == 0) && (d->so_x % 8 == 0) && (d->so_c1 % 8 == 0) &&
              ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) &&
@@ -1176,29 +1247,6 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
       }
     }
   }
-  // ---- B-resident mode (small-K GEMMs are L2->SM traffic bound): plain (1 segment, 1 tap, shared weights, no
-  //      split) GEMMs whose [BN x K] weight tile fits beside a 4-stage A ring keep it in shared memory for all
-  //      tiles of the CTA; requires n_tile fixed per CTA (grid = multiple of n_tiles).
-  p.b_resident = 0;
-  if (d->nseg == 1 && d->taps[0] == 1 && !p.b_batched && p.splits == 1 && gemm_bres_enabled()) {
-    const int try_bn[1] = {BNsel};     // (switching to a narrower tile to make the weights fit measured slower)
-    for (int i = 0; i < 1; ++i) {
-      const int bn_c = try_bn[i];
-      if (d->bn_force && bn_c != d->bn_force) continue;
-      if (geglu && (d->N % bn_c)) continue;
-      const long long nt = cdivll(d->N, bn_c);
-      if (nt > sms || m_tiles * nt < 2LL * sms) continue;
-      const size_t tile_b = (size_t)bn_c * BK * 2;
-      const size_t raw = (size_t)(SMEM_BUDGET - smem_fixed(bn_c)) / (STAGE_A_BYTES + tile_b);
-      const size_t total_smem = (raw > 8 ? 8 : raw) * (STAGE_A_BYTES + tile_b);
-      if ((size_t)num_kb * tile_b + 4u * STAGE_A_BYTES <= total_smem) {
-        p.b_resident = 1;
-        BNsel = bn_c;
-        p.n_tiles = (int)nt;
-        break;
-      }
-    }
-  }
   {
     const long long nbatch = p.b_batched ? d->NB : 1;
     cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)nbatch};
@@ -1211,7 +1259,6 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
 
   const long long total = m_tiles * p.n_tiles * p.splits;
   int grid = (int)(total < sms ? total : sms);
-  if (p.b_resident) grid = (sms / p.n_tiles) * p.n_tiles;   // n_tile fixed per CTA
   int rc;
   switch (BNsel) {
     case 64: rc = launch_gemm<64>(p, grid, st); break;

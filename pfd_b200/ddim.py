@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import native as nv
-from .graphs import weights_signature
+from .graphs import capture as graph_capture, weights_signature
 
 
 def eta_is_zero(sigmas) -> bool:
@@ -306,12 +306,12 @@ class _SamplerState:
             torch.cuda.synchronize()
             self.prep_graph = torch.cuda.CUDAGraph()
             n0 = nv.launch_count()
-            with torch.cuda.graph(self.prep_graph):
+            with graph_capture(self.prep_graph):
                 self._prepare()
             self.n_prep = nv.launch_count() - n0
             self.step_graph = torch.cuda.CUDAGraph()
             n0 = nv.launch_count()
-            with torch.cuda.graph(self.step_graph):
+            with graph_capture(self.step_graph):
                 for _ in range(self.spg):
                     self._one_step()
             self.n_step = nv.launch_count() - n0

@@ -6,12 +6,30 @@ the request path.  Graphs are keyed on input shapes and on a signature of the we
 """
 from __future__ import annotations
 
+import contextlib
+import gc
 from typing import Callable, Dict, Hashable, List, Sequence, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import native as nv
+
+
+@contextlib.contextmanager
+def capture(graph: "torch.cuda.CUDAGraph"):
+    """torch.cuda.graph(graph) with the Python garbage collector held off: a cyclic-garbage sweep in the middle of a
+    capture may run the destructor of an older CUDAGraph (cudaGraphExecDestroy), which is illegal while a stream
+    is capturing in the global capture mode and invalidates the capture."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was:
+            gc.enable()
 
 
 _generation = 0
@@ -69,7 +87,7 @@ class GraphedFunction:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = nv.launch_count()
-        with torch.cuda.graph(self.graph):
+        with capture(self.graph):
             self.static_out = fn(*self.static_in)
         self.n_kernels = nv.launch_count() - n0
 

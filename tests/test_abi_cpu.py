@@ -35,8 +35,23 @@ def test_gemm_desc_layout_matches_header():
     from pfd_b200 import native
     d = native.GemmDesc()
     # 1+3+3 int32 (=28, pad to 32) + 3 ptr + 9 int64 + 6 int32 + ptr + int32(+pad) + 2 int64 + float + int32
-    # + 4 ptr + 6 int64 + 3 int32 (+pad) + ptr
-    assert ctypes.sizeof(d) == 32 + 24 + 72 + 24 + 8 + 8 + 16 + 8 + 40 + 48 + 16 + 8
+    # + 4 ptr + 6 int64 + 4 int32 (ndiv, cdiv, bn_force, tap_off) + stats_out ptr + stats_unit int32 (+pad) + stream ptr
+    assert ctypes.sizeof(d) == 32 + 24 + 72 + 24 + 8 + 8 + 16 + 8 + 40 + 48 + 16 + 8 + 8 + 8
+    # and the same field order as the header declares
+    import re
+    src = open(os.path.join(ROOT, "include", "pfd_b200.h")).read()
+    start = "typedef struct pfd_gemm_desc {"
+    body = src[src.index(start) + len(start):src.index("} pfd_gemm_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            m = re.search(r"(\w+)\s*(\[\w+\])?\s*$", part.strip())
+            names.append(m.group(1))
+    assert names == [f[0] for f in native.GemmDesc._fields_], (names, [f[0] for f in native.GemmDesc._fields_])
 
 
 def test_bad_descriptor_is_rejected_without_gpu():

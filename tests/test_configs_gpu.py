@@ -228,7 +228,7 @@ def test_reference_fp16_floor(env):
         pytest.skip("baseline/_ref not staged")
     cwd = os.getcwd()
     try:
-        ref, _ = rh.build_reference_net("pfd_seecoder", device="cuda")
+        ref, _ = rh.build_reference_net("pfd_seecoder", fast=True)
         rh.fill_reference_net(ref)
         ref = ref.half()
         ref.to("cuda")

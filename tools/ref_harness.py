@@ -93,8 +93,8 @@ def import_reference():
     if REF is None:
         raise RuntimeError("reference tree not found (neither /root/reference nor baseline/_ref)")
     install_shims()
+    os.chdir(REF)                       # cfg_helper resolves 'configs/model' relative to the CWD on every call
     if not _imported:
-        os.chdir(REF)
         sys.path.insert(0, REF)
         _imported = True
     from lib.cfg_helper import model_cfg_bank
@@ -102,10 +102,31 @@ def import_reference():
     return model_cfg_bank, get_model
 
 
-def build_reference_net(name="pfd_seecoder_with_controlnet", overrides=None, device=None):
-    """Build the reference pipeline (random init).  `overrides(cfgm)` may shrink the config.  device: construct
-    the parameters directly on that device (torch.device context) - random init of 1.6 B parameters takes ~50 s on
-    8 CPU cores and milliseconds on the GPU."""
+class skip_random_init:
+    """Make torch.nn.init.* no-ops while the reference constructs its modules: random initialisation of 1.6 B
+    parameters takes ~40 s on 8 CPU cores and every floating-point tensor is overwritten by fill_reference_net()
+    anyway.  (Construction must stay on the CPU: register_schedule calls .numpy() on freshly created tensors,
+    diffusion_utils.py:30, so a torch.device('cuda') context breaks it.)"""
+    NAMES = ("uniform_", "normal_", "trunc_normal_", "constant_", "ones_", "zeros_", "xavier_uniform_",
+             "xavier_normal_", "kaiming_uniform_", "kaiming_normal_", "orthogonal_")
+
+    def __enter__(self):
+        import torch
+        self.saved = {n: getattr(torch.nn.init, n) for n in self.NAMES if hasattr(torch.nn.init, n)}
+        for n in self.saved:
+            setattr(torch.nn.init, n, lambda tensor, *a, **k: tensor)
+        return self
+
+    def __exit__(self, *e):
+        import torch
+        for n, f in self.saved.items():
+            setattr(torch.nn.init, n, f)
+
+
+def build_reference_net(name="pfd_seecoder_with_controlnet", overrides=None, device=None, fast=False):
+    """Build the reference pipeline on the CPU.  `overrides(cfgm)` may shrink the config.  fast=True skips the random
+    initialisation (use only when fill_reference_net() follows).  `device` is accepted for callers that move the
+    net afterwards; construction itself is always on the CPU."""
     import contextlib
     import torch
     model_cfg_bank, get_model = import_reference()
@@ -114,8 +135,7 @@ def build_reference_net(name="pfd_seecoder_with_controlnet", overrides=None, dev
     if overrides is not None:
         overrides(cfgm)
     torch.manual_seed(0)
-    ctx = torch.device(device) if device is not None else contextlib.nullcontext()
-    with ctx:
+    with (skip_random_init() if fast else contextlib.nullcontext()):
         net = get_model()(cfgm)
     net.eval()
     return net, cfgm
