@@ -110,6 +110,9 @@ PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d);
 /* 1 if the last pfd_gemm_f16 call of this thread wrote d->stats_out (0: unsupported tiling / epilogue -> the
  * consumer must compute its own statistics). */
 PFD_API int pfd_gemm_stats_written(void);
+/* Tuning switches for A/B measurements inside one process.  "gemm_epilogue_warps": 0 = automatic (default), 8 / 16 =
+ * force that epilogue variant of the lean GEMM path. */
+PFD_API int pfd_set_option(const char* name, int32_t value);
 
 /*
  * GroupNorm(32 groups) [+ SiLU] over channel-last fp16, optionally over the channel-concatenation

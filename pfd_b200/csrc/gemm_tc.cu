@@ -1065,6 +1065,7 @@ static inline bool gemm_lean_enabled() {
 }
 
 thread_local int g_last_stats = 0;
+int g_ew_mode = -1;            // epilogue-warp policy: -1 = read PFD_GEMM_EW once, 0 = automatic, 8 / 16 = forced
 
 template <int BN>
 static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream) {
@@ -1088,11 +1089,11 @@ static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream) {
   if (!lean) return launch_gemm_t<BN, false, 8>(p, grid, stream);
   // 16 epilogue warps where the epilogue bounds the tile: per 128 x BN tile the MMA takes ~num_kb * 2 * BN cycles,
   // the 8-warp epilogue ~3400 (plain) to ~5000 (GEGLU) cycles (r1 ncu source-page measurements)
-  static int ew_mode = -1;      // PFD_GEMM_EW: 8 / 16 force the variant, anything else = automatic
-  if (ew_mode < 0) {
+  if (g_ew_mode < 0) {          // PFD_GEMM_EW: 8 / 16 force the variant, anything else = automatic
     const char* e = getenv("PFD_GEMM_EW");
-    ew_mode = e ? atoi(e) : 0;
+    g_ew_mode = e ? atoi(e) : 0;
   }
+  const int ew_mode = g_ew_mode;
   const long long mma_cycles = (long long)p.num_kb * 2 * BN;
   const long long epi_cycles = p.act == PFD_ACT_GEGLU ? 5200 : 3400;
   const bool wide = !stats_ok && (ew_mode == 16 || (ew_mode != 8 && mma_cycles < epi_cycles * 3 / 2));
@@ -1104,6 +1105,15 @@ static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream) {
 using namespace pfd;
 
 extern "C" PFD_API int pfd_gemm_stats_written(void) { return g_last_stats; }
+
+extern "C" PFD_API int pfd_set_option(const char* name, int32_t value) {
+  if (name && !strcmp(name, "gemm_epilogue_warps")) {
+    if (value != 0 && value != 8 && value != 16) return set_error("pfd_set_option: gemm_epilogue_warps must be 0, 8 or 16");
+    g_ew_mode = value;
+    return 0;
+  }
+  return set_error("pfd_set_option: unknown option '%s'", name ? name : "(null)");
+}
 
 extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   if (!d) return set_error("pfd_gemm_f16: null descriptor");

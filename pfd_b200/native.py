@@ -23,7 +23,7 @@ PFD_MAX_SEG = 3
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_RELU, ACT_GEGLU = 0, 1, 2, 3, 4
 
 EXPORTS = [
-    "pfd_version", "pfd_last_error", "pfd_launch_count", "pfd_gemm_f16", "pfd_gemm_stats_written", "pfd_groupnorm_f16",
+    "pfd_version", "pfd_last_error", "pfd_launch_count", "pfd_gemm_f16", "pfd_gemm_stats_written", "pfd_set_option", "pfd_groupnorm_f16",
     "pfd_layernorm_f16", "pfd_softmax_f16", "pfd_timestep_embedding_f16", "pfd_upsample2x_f16",
     "pfd_nchw_to_nhwc_f16", "pfd_nhwc_to_nchw_f16", "pfd_im2col3x3_f16", "pfd_axpby_f16",
     "pfd_add_rowvec_f16", "pfd_ddim_step_f16", "pfd_window_gather_f16", "pfd_window_scatter_f16",
@@ -89,6 +89,7 @@ def load() -> ctypes.CDLL:
                                       c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                       c_void_p, c_int32, c_void_p]
     lib.pfd_gemm_stats_written.argtypes = []
+    lib.pfd_set_option.argtypes = [c_char_p, c_int32]
     lib.pfd_layernorm_f16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_float,
                                       c_void_p, c_void_p]
     lib.pfd_softmax_f16.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int64, c_float, c_void_p,
@@ -140,6 +141,11 @@ def _check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().pfd_last_error()
         raise RuntimeError(f"{what} failed: {msg.decode() if msg else rc}")
+
+
+def set_option(name: str, value: int) -> None:
+    """Library tuning switch (see pfd_set_option)."""
+    _check(load().pfd_set_option(name.encode(), int(value)), "pfd_set_option")
 
 
 def stream_ptr() -> int:
