@@ -45,6 +45,9 @@ PFD_API int pfd_version(void);
 PFD_API const char* pfd_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py: gpu_launches) */
 PFD_API int64_t pfd_launch_count(void);
+/* Run-time tuning switches, so that variants can be A/B-timed inside one process (tools/ab_unet.py); name == NULL
+ * resets all of them to the built-in defaults.  Unknown names are stored and ignored. */
+PFD_API int pfd_set_option(const char* name, int32_t value);
 
 /*
  * pfd_gemm_f16 — the tcgen05 tensor-core contraction used for every Linear, 1x1 conv, 3x3 conv
@@ -98,22 +101,10 @@ typedef struct pfd_gemm_desc {
   int32_t bn_force;          /* 0 = library picks the N tile; else one of 64/128/160/192/256 (GEGLU packing) */
   int32_t tap_off;           /* 3x3 taps read A at (y*s + dy - 1 + tap_off): 0 = symmetric padding 1; 1 = the VAE
                                 encoder's F.pad(x,(0,1,0,1)) + stride-2 conv with padding 0 (autokl_modules.py:69-76) */
-  void* stats_out;           /* optional fp32 [NB, N/stats_unit, 2], PRE-ZEROED: the epilogue adds the sum and the sum
-                                of squares of the final fp16 outputs per (image, unit of stats_unit channels), so the
-                                consuming GroupNorm (pfd_groupnorm_f16 stats1/stats2) needs no statistics pass.  Best
-                                effort: pfd_gemm_stats_written() tells whether this call produced them. */
-  int32_t stats_unit;        /* channels per unit: 4 or >= 8, dividing N and the consumer's channels-per-group */
   void* stream;
 } pfd_gemm_desc;
 
 PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d);
-/* 1 if the last pfd_gemm_f16 call of this thread wrote d->stats_out (0: unsupported tiling / epilogue -> the
- * consumer must compute its own statistics). */
-PFD_API int pfd_gemm_stats_written(void);
-/* Tuning switches for A/B measurements inside one process.  "gemm_epilogue_warps": 0 = automatic (default), 8 / 16 =
- * force that epilogue variant of the lean GEMM path. */
-PFD_API int pfd_set_option(const char* name, int32_t value);
-
 /*
  * GroupNorm(32 groups) [+ SiLU] over channel-last fp16, optionally over the channel-concatenation
  * of two tensors (the UNet skip concat, pfd.py:356,519) — writes one contiguous [NB,H,W,C1+C2].
@@ -124,14 +115,10 @@ PFD_API int pfd_set_option(const char* name, int32_t value);
  *     32-bit arrival counter per image for the single-pass kernel),
  *     16-byte aligned.  zero_ws != 0: the call zeroes it first (one extra memset node); zero_ws == 0: the
  *     caller guarantees it is already zero (e.g. one bulk memset of many slots per network evaluation).
- * stats1 / stats2 (optional): per-(image, unit) fp32 {sum, sum of squares} of x1 / x2 written by the producing
- *     pfd_gemm_f16 epilogues (layout [NB, c/stats_unit, 2]); when given for every input, the statistics pass is
- *     skipped and the call is a single streaming normalise(+SiLU) kernel.  stats_unit must divide c1, c2 and C/groups.
  */
 PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, int32_t NB,
                       int64_t HW, int32_t groups, const void* gamma, const void* beta, float eps,
-                      int32_t silu, void* out, float* ws, int32_t zero_ws, const float* stats1,
-                      const float* stats2, int32_t stats_unit, void* stream);
+                      int32_t silu, void* out, float* ws, int32_t zero_ws, void* stream);
 
 /* LayerNorm over the last dim of [rows, C] fp16 (attention.py:294-296, swin.py norms, seecoder.py norms).
  * Optional fused residual: out = LN(x + res) (post-norm layers of seecoder.py:85-90,135-136). */

@@ -114,21 +114,18 @@ class Decoder(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------
-VAE_GN_UNIT = 4          # ch = 128: GroupNorm(32) groups of 4 / 8 / 16 channels are whole numbers of 4-channel units
-
-
 def run_vae_resnet(rb: ResnetBlock, x: torch.Tensor) -> torch.Tensor:
     g, b = pk_norm(rb.norm1)
     h = nv.groupnorm(x, g, b, rb.norm1.eps, silu=True)
     w, bb = pk_conv3(rb.conv1)
-    h = nv.conv3x3(h, w, bb, stats_unit=VAE_GN_UNIT)
+    h = nv.conv3x3(h, w, bb)
     g, b = pk_norm(rb.norm2)
     h = nv.groupnorm(h, g, b, rb.norm2.eps, silu=True)
     if rb.in_channels != rb.out_channels:
         w, bb = pk_conv3(rb.conv2, rb.nin_shortcut)
-        return nv.conv3x3(h, w, bb, skip=[x], stats_unit=VAE_GN_UNIT)
+        return nv.conv3x3(h, w, bb, skip=[x])
     w, bb = pk_conv3(rb.conv2)
-    return nv.conv3x3(h, w, bb, residual=x, stats_unit=VAE_GN_UNIT)
+    return nv.conv3x3(h, w, bb, residual=x)
 
 
 def run_vae_attn(at: AttnBlock, x: torch.Tensor) -> torch.Tensor:
@@ -157,8 +154,7 @@ def run_vae_attn(at: AttnBlock, x: torch.Tensor) -> torch.Tensor:
         nv.softmax_(sc, float(C) ** -0.5)
         nv.bmm_nt(sc, vt, out=o[:, r0:r0 + rows], so=(N * C, 0, 0, C, 0, 1))
     w, bb = pk_lin(at.proj_out)
-    o2 = nv.linear(o.reshape(B * N, C), w, bb, residual=x.reshape(B * N, C), stats_unit=VAE_GN_UNIT)
-    return nv.carry_stats(o2.reshape(B, H, W, C), o2)
+    return nv.linear(o.reshape(B * N, C), w, bb, residual=x.reshape(B * N, C)).reshape(B, H, W, C)
 
 
 class AutoencoderKL(nn.Module):
@@ -193,7 +189,7 @@ class AutoencoderKL(nn.Module):
                 h = run_vae_resnet(rb, h)
             if lvl != enc.num_resolutions - 1:
                 w, b = pk_conv3(enc.down[lvl].downsample.conv)
-                h = nv.conv3x3(h, w, b, stride=2, tap_off=1, stats_unit=VAE_GN_UNIT)
+                h = nv.conv3x3(h, w, b, stride=2, tap_off=1)
         h = run_vae_resnet(enc.mid.block_1, h)
         h = run_vae_attn(enc.mid.attn_1, h)
         h = run_vae_resnet(enc.mid.block_2, h)
@@ -231,7 +227,7 @@ class AutoencoderKL(nn.Module):
                 h = run_vae_resnet(rb, h)
             if lvl != 0:
                 w, b = pk_conv3(up.upsample.conv)
-                h = nv.conv3x3(nv.upsample2x(h), w, b, stats_unit=VAE_GN_UNIT)
+                h = nv.conv3x3(nv.upsample2x(h), w, b)
         g, b = pk_norm(dec.norm_out)
         h = nv.groupnorm(h, g, b, dec.norm_out.eps, silu=True)
         w, b = pk_conv3(dec.conv_out)                                      # rows padded 3 -> 8

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import native as nv
 from .modules import Conv2d, IndexedSequential, Linear, pk_conv3, pk_conv3_small, pk_lin
-from .unet import (Downsample, ResBlock, SpatialTransformer, batched_emb_layers, context_kv, gn_unit, run_resblock,
+from .unet import (Downsample, ResBlock, SpatialTransformer, batched_emb_layers, context_kv, run_resblock,
                    run_spatial_transformer, time_embed_silu)
 
 _HINT_STEM = [(16, 1), (16, 1), (32, 2), (32, 1), (96, 2), (96, 1), (256, 2)]
@@ -129,17 +129,16 @@ class ControlNet(nn.Module):
         kv_of = {id(st): kvi for st, kvi in zip(self._transformers(), kv)}
         guided = hint_feat if hint_feat is not None else self.hint_features(hint)
         outs = []
-        unit = gn_unit(self.model_channels)
         h = nv.nchw_to_nhwc(x)
         for bi, blk in enumerate(self.input_blocks):
             for layer in blk:
                 if isinstance(layer, ResBlock):
-                    h = run_resblock(layer, h, None, embs[id(layer)], unit)
+                    h = run_resblock(layer, h, None, embs[id(layer)])
                 elif isinstance(layer, SpatialTransformer):
-                    h = run_spatial_transformer(layer, h, context, kv_of[id(layer)], unit)
+                    h = run_spatial_transformer(layer, h, context, kv_of[id(layer)])
                 elif isinstance(layer, Downsample):
                     w, b = pk_conv3(layer.op)
-                    h = nv.conv3x3(h, w, b, stride=2, stats_unit=unit)
+                    h = nv.conv3x3(h, w, b, stride=2)
                 elif isinstance(layer, Conv2d):
                     w, b, kpad = pk_conv3_small(layer)
                     B, H, W, _ = h.shape
@@ -155,9 +154,9 @@ class ControlNet(nn.Module):
                 guided = None
             w, b = pk_lin(self.zero_convs[bi][0])
             outs.append(nv.conv1x1(h, w, b))
-        h = run_resblock(self.middle_block[0], h, None, embs[id(self.middle_block[0])], unit)
-        h = run_spatial_transformer(self.middle_block[1], h, context, kv_of[id(self.middle_block[1])], unit)
-        h = run_resblock(self.middle_block[2], h, None, embs[id(self.middle_block[2])], unit)
+        h = run_resblock(self.middle_block[0], h, None, embs[id(self.middle_block[0])])
+        h = run_spatial_transformer(self.middle_block[1], h, context, kv_of[id(self.middle_block[1])])
+        h = run_resblock(self.middle_block[2], h, None, embs[id(self.middle_block[2])])
         w, b = pk_lin(self.middle_block_out[0])
         outs.append(nv.conv1x1(h, w, b))
         return outs

@@ -14,6 +14,8 @@ extern thread_local std::string g_last_error;
 extern std::atomic<int64_t> g_launches;
 
 int set_error(const char* fmt, ...);
+// run-time tuning switch set through pfd_set_option (A/B measurements inside one process); dflt when unset
+int option(const char* name, int dflt);
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaPeekAtLastError();

@@ -152,15 +152,12 @@ gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   }
 }
 
-// PRE = true: the group statistics come from the producing GEMM epilogues (fp32 {sum, sumsq} per (image, unit of
-// `unit` channels) of x1 / x2, see pfd_gemm_desc.stats_out) instead of gn_stats_kernel's fp64 workspace.
-template <bool PRE>
 __global__ void __launch_bounds__(320)
 gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2,
                 long long HW, int groups, const __half* __restrict__ gamma,
                 const __half* __restrict__ beta, float eps, int silu,
                 const double* __restrict__ ws, __half* __restrict__ out, long long pix_per_cta,
-                double inv_cnt, const float* __restrict__ st1, const float* __restrict__ st2, int unit) {
+                double inv_cnt) {
   pdl_enter();
   const int C = c1 + c2;
   const int cpg = C / groups;
@@ -186,20 +183,8 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
         const int g = (c + i) / cpg;
         if (g != gprev) {
           // fp64 only for the cancellation-prone E[x^2] - mean^2 (3 DP ops, no DP division)
-          double s_sum, s_sq;
-          if (PRE) {
-            s_sum = 0.0;
-            s_sq = 0.0;
-            for (int cc = g * cpg; cc < (g + 1) * cpg; cc += unit) {
-              const float* u = cc < c1 ? st1 + ((long long)n * (c1 / unit) + cc / unit) * 2
-                                       : st2 + ((long long)n * (c2 / unit) + (cc - c1) / unit) * 2;
-              s_sum += (double)__ldg(u);
-              s_sq += (double)__ldg(u + 1);
-            }
-          } else {
-            s_sum = ws[((long long)n * groups + g) * 2 + 0];
-            s_sq = ws[((long long)n * groups + g) * 2 + 1];
-          }
+          const double s_sum = ws[((long long)n * groups + g) * 2 + 0];
+          const double s_sq = ws[((long long)n * groups + g) * 2 + 1];
           const double m = s_sum * inv_cnt;
           double var = s_sq * inv_cnt - m * m;
           if (var < 0) var = 0;
@@ -680,16 +665,12 @@ using namespace pfd;
 
 extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void* x2, int32_t c2, int32_t NB,
                                  int64_t HW, int32_t groups, const void* gamma, const void* beta,
-                                 float eps, int32_t silu, void* out, float* ws, int32_t zero_ws,
-                                 const float* stats1, const float* stats2, int32_t stats_unit, void* stream) {
+                                 float eps, int32_t silu, void* out, float* ws, int32_t zero_ws, void* stream) {
   const int C = c1 + (x2 ? c2 : 0);
   if (!x2) c2 = 0;
   if (groups <= 0 || groups > GN_MAX_GROUPS || C % groups) return set_error("pfd_groupnorm_f16: C=%d groups=%d", C, groups);
   if (c1 % 8 || c2 % 8) return set_error("pfd_groupnorm_f16: channel counts must be multiples of 8 (%d,%d)", c1, c2);
-  const bool pre = stats1 != nullptr && (x2 == nullptr || stats2 != nullptr);
-  if (pre && (stats_unit <= 0 || c1 % stats_unit || (x2 && c2 % stats_unit) || (C / groups) % stats_unit))
-    return set_error("pfd_groupnorm_f16: stats_unit %d does not divide c1=%d c2=%d cpg=%d", stats_unit, c1, c2, C / groups);
-  if (!ws && !pre) return set_error("pfd_groupnorm_f16: workspace required");
+  if (!ws) return set_error("pfd_groupnorm_f16: workspace required");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* dws = reinterpret_cast<double*>(ws);
   const int vecs = C / 8;
@@ -697,7 +678,7 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   int threads = vecs <= 320 ? (vecs <= 256 ? (256 / vecs) * vecs : vecs) : 256;
   if (threads < 64) threads = vecs * ((64 + vecs - 1) / vecs);
   const double inv_cnt = 1.0 / ((double)HW * (C / groups));
-  if (zero_ws && !pre) cudaMemsetAsync(dws, 0, sizeof(double) * 2 * NB * groups, st);
+  if (zero_ws) cudaMemsetAsync(dws, 0, sizeof(double) * 2 * NB * groups, st);
   // ~3 CTAs per SM, but at least 16 pixels per pixel-lane so the per-CTA setup is amortised
   long long chunks = (3LL * num_sms() + NB - 1) / NB;
   long long ppc = (HW + chunks - 1) / chunks;
@@ -705,20 +686,13 @@ extern "C" PFD_API int pfd_groupnorm_f16(const void* x1, int32_t c1, const void*
   if (ppc < min_ppc) ppc = min_ppc;
   chunks = (HW + ppc - 1) / ppc;
   dim3 grid((unsigned)chunks, (unsigned)NB);
-  if (pre) {
-    launch_k(gn_apply_kernel<true>, dim3(grid), dim3(threads), (size_t)(0), st, static_cast<const __half*>(x1), (int)c1,
-             static_cast<const __half*>(x2), (int)c2, (long long)HW, (int)groups, static_cast<const __half*>(gamma),
-             static_cast<const __half*>(beta), eps, (int)silu, (const double*)nullptr, static_cast<__half*>(out),
-             (long long)ppc, inv_cnt, stats1, stats2, (int)stats_unit);
-    return check_launch("gn_apply_pre");
-  }
   launch_k(gn_stats_kernel, dim3(grid), dim3(threads), (size_t)(0), st, static_cast<const __half*>(x1), c1, static_cast<const __half*>(x2), c2,
                                             HW, groups, ppc, dws);
   if (int rc = check_launch("gn_stats")) return rc;
-  launch_k(gn_apply_kernel<false>, dim3(grid), dim3(threads), (size_t)(0), st, static_cast<const __half*>(x1), (int)c1,
+  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), (size_t)(0), st, static_cast<const __half*>(x1), (int)c1,
            static_cast<const __half*>(x2), (int)c2, (long long)HW, (int)groups, static_cast<const __half*>(gamma),
            static_cast<const __half*>(beta), eps, (int)silu, (const double*)dws, static_cast<__half*>(out), (long long)ppc,
-           inv_cnt, (const float*)nullptr, (const float*)nullptr, 0);
+           inv_cnt);
   return check_launch("gn_apply");
 }
 

@@ -25,14 +25,13 @@ namespace pfd {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-// threads = TMA warp + MMA warp + EW epilogue warps (EW = 8: 320 threads, up to 168 registers; EW = 16: 576 threads,
-// 112 registers - for the launches whose epilogue, not the MMA, bounds the tile time: small-K Linears, GEGLU)
-constexpr int gemm_threads(int ew) { return 64 + 32 * ew; }
+constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STAGE_A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int SMEM_BUDGET = 232448;         // 227 KiB opt-in limit per CTA
+constexpr int EPI_WARPS = 8;
 constexpr int EPI_STG_BYTES = 1024;         // per epilogue warp: 16 rows x 64 B transpose buffer
 // alignment slack + barriers + epilogue transpose buffers + fp32 bias of the tile (double-buffered)
-constexpr int smem_fixed(int bn, int ew) { return 1024 + 256 + ew * EPI_STG_BYTES + 2 * bn * 4; }
+constexpr int smem_fixed(int bn) { return 1024 + 256 + EPI_WARPS * EPI_STG_BYTES + 2 * bn * 4; }
 
 struct alignas(64) GemmParams {
   CUtensorMap tmA[PFD_MAX_SEG];
@@ -61,17 +60,15 @@ struct alignas(64) GemmParams {
   long long rowadd_ld;
   int ndiv, cdiv;
   int vec_ok;
-  float* stats;      // optional [NB][N / stats_unit][2] fp32 (sum, sum of squares) of the final fp16 outputs
-  int stats_unit;    // channels per statistics unit (GroupNorm statistics from the producer epilogue)
 };
 
-template <int BN, int EW>
+template <int BN>
 struct GemmCfg {
   static constexpr int STAGE_B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-  static constexpr int RAW_STAGES = (SMEM_BUDGET - smem_fixed(BN, EW)) / STAGE_BYTES;
+  static constexpr int RAW_STAGES = (SMEM_BUDGET - smem_fixed(BN)) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + smem_fixed(BN, EW);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + smem_fixed(BN);
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128u : (2 * BN <= 256 ? 256u : 512u);
   static_assert(STAGE_B_BYTES % 1024 == 0, "B stage must keep 1024-B swizzle alignment");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
@@ -163,12 +160,10 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 // LEAN = true: epilogue for 16-byte-vectorisable outputs (channel-last rows, optional head split) without split-K;
 // LEAN = false keeps the general path (element-strided outputs such as V^T, split-K partials).
-template <int BN, bool LEAN, int EW>
-__global__ void __launch_bounds__(gemm_threads(EW), 1)
+template <int BN, bool LEAN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, EW>;
-  constexpr int EPI_WARPS = EW;
-  constexpr int NPART = EW / 4;             // epilogue warps per TMEM lane quarter (each takes a share of the columns)
+  using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
 
@@ -202,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 32 * EW);
+      mbar_init(tempty_bar(a), 256);
     }
     mbar_fence_init();
   }
@@ -306,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     // 16 columns).  Per chunk all global loads (bias / row add / residual) are issued before the
     // TMEM load is waited on, index arithmetic is hoisted out of the chunk loop.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half_id = (warp - 2) >> 2;    // column share of this warp: 0 .. NPART-1
+    const int half_id = (warp - 2) >> 2;    // 0: warps 2..5, 1: warps 6..9
     const int row = q * 32 + lane;
     const int rdx = row % p.bw;
     const int rdy = (row / p.bw) % p.bh;
@@ -316,8 +311,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     constexpr int CB = BN;                  // accumulator columns per tile in TMEM
     const int ocols = geglu ? CB / 2 : CB;  // output columns this tile produces
     const int nch = ocols / 16;
-    const int ch_begin = (nch * half_id + NPART - 1) / NPART;
-    const int ch_end = (nch * (half_id + 1) + NPART - 1) / NPART;
+    const int ch_begin = half_id == 0 ? 0 : (nch + 1) / 2;
+    const int ch_end = half_id == 0 ? (nch + 1) / 2 : nch;
     const bool plain_cols = p.cdiv >= p.N;  // no head split: column offset = col * so_c0
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
@@ -407,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         };
         if (geglu) {
           // ------ GEGLU: out[:, col] = value * gelu(gate), runs of 16 output columns (value + gate accumulators)
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           mbar_wait(tfull_bar(as), aph);
           tc_fence_after();
           const uint32_t wr16 = stg + lane * 32;
@@ -451,65 +446,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           mbar_arrive(tempty_bar(as));
           continue;
         }
-        // GroupNorm statistics of the tile's FINAL fp16 values (after bias / row add / activation / residual), per
-        // (image, unit of `stats_unit` channels): accumulated per lane over the rows it stores, folded into the (at
-        // most two) units its 8 columns touch, reduced over the lanes that hold the same columns and added to the
-        // fp32 workspace with one atomic pair per unit per warp and run.  All 32 rows of a warp belong to one image
-        // (the host enables this only when bw * bh >= 32).
-        const bool do_stats = (EW == 8) && p.stats != nullptr;
-        const int st_unit = p.stats_unit > 0 ? p.stats_unit : 8;
-        const int st_n = tn * p.bn + (q * 32) / (p.bw * p.bh);
-        float ssum[8], ssq[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = 0.f;
-        auto stats_add = [&](const uint4& o) {
-          const __half2* hh = reinterpret_cast<const __half2*>(&o);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(hh[i]);
-            ssum[2 * i] += f.x;
-            ssum[2 * i + 1] += f.y;
-            ssq[2 * i] = fmaf(f.x, f.x, ssq[2 * i]);
-            ssq[2 * i + 1] = fmaf(f.y, f.y, ssq[2 * i + 1]);
-          }
-        };
-        // lanes_per_row = 4 (32-column runs) or 2 (16-column run); c = first of this lane's 8 output columns
-        auto stats_flush = [&](int c, int lanes_per_row, bool colok) {
-          const int u0 = c / st_unit;
-          const int sp = min(8, (u0 + 1) * st_unit - c);
-          float a0 = 0.f, q0 = 0.f, a1 = 0.f, q1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < sp) {
-              a0 += ssum[i];
-              q0 += ssq[i];
-            } else {
-              a1 += ssum[i];
-              q1 += ssq[i];
-            }
-            ssum[i] = ssq[i] = 0.f;
-          }
-          for (int off = lanes_per_row; off < 32; off <<= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, off);
-            q0 += __shfl_xor_sync(0xffffffffu, q0, off);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-            q1 += __shfl_xor_sync(0xffffffffu, q1, off);
-          }
-          if (lane < lanes_per_row && colok && st_n < p.NB) {
-            float* sp0 = p.stats + ((long long)st_n * (n_lim / st_unit) + u0) * 2;
-            atomicAdd(sp0, a0);
-            atomicAdd(sp0 + 1, q0);
-            if (sp < 8 && c + sp < n_lim) {
-              atomicAdd(sp0 + 2, a1);
-              atomicAdd(sp0 + 3, q1);
-            }
-          }
-        };
         uint4 ra[4], rb[4];
         int c0 = cbeg;
         if (n32 > 0) load_res32(c0, ra);
         else if (tail16) load_res16(c0, ra);
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");   // bias of this tile visible to all epilogue warps
+        asm volatile("bar.sync 1, 256;" ::: "memory");            // bias of this tile visible to all epilogue warps
         mbar_wait(tfull_bar(as), aph);
         tc_fence_after();
         const uint32_t wr32 = stg + (lane & 15) * 64;
@@ -578,15 +519,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
                 uint4 o = ld_shared_v4(rd32 + it * 512);
                 if (has_res) o = hadd2x4(o, ra[j]);
                 *reinterpret_cast<uint4*>(p.out + roff4[j] + co) = o;
-                if constexpr (EW == 8) {
-                  if (do_stats) stats_add(o);
-                }
               }
             }
             __syncwarp();
-          }
-          if constexpr (EW == 8) {
-            if (do_stats) stats_flush(c, 4, colok);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) ra[j] = rb[j];
@@ -638,14 +573,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
                 uint4 o = ld_shared_v4(stg + rr * 32 + ((cc2 ^ ((rr >> 2) & 1)) << 4));
                 if (has_res) o = hadd2x4(o, ra[it]);
                 *reinterpret_cast<uint4*>(p.out + roff2[it] + co) = o;
-                if constexpr (EW == 8) {
-                  if (do_stats) stats_add(o);
-                }
               }
             }
-          }
-          if constexpr (EW == 8) {
-            if (do_stats) stats_flush(c, 2, c < n_lim);
           }
           __syncwarp();
         }
@@ -1041,17 +970,17 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
 
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
-template <int BN, bool LEAN, int EW>
+template <int BN, bool LEAN>
 static int launch_gemm_t(const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, EW>;
+  using Cfg = GemmCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN, EW>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_done = true;
   }
-  launch_k(gemm_tc_kernel<BN, LEAN, EW>, dim3(grid), dim3(gemm_threads(EW)), Cfg::SMEM_BYTES, stream, p);
+  launch_k(gemm_tc_kernel<BN, LEAN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
   return check_launch("pfd_gemm_f16");
 }
 
@@ -1064,18 +993,9 @@ static inline bool gemm_lean_enabled() {
   return v == 1;
 }
 
-thread_local int g_last_stats = 0;
-int g_ew_mode = -1;            // epilogue-warp policy: -1 = read PFD_GEMM_EW once, 0 = automatic, 8 / 16 = forced
-
 template <int BN>
-static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream) {
+static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
   const bool lean = gemm_lean_enabled() && p.vec_ok && p.splits == 1;
-  // producer-side GroupNorm statistics: lean 8-warp epilogue only, plain channel-last output columns, every warp's
-  // 32 rows inside one image, at most two units per 8-column vector
-  const bool stats_ok = lean && p.stats != nullptr && p.act != PFD_ACT_GEGLU && p.cdiv >= p.N && p.bw * p.bh >= 32 &&
-                        (p.stats_unit == 4 || p.stats_unit >= 8) && p.N % p.stats_unit == 0;
-  if (!stats_ok) p.stats = nullptr;
-  g_last_stats = stats_ok ? 1 : 0;
   static int trace = -1;
   if (trace < 0) {
     const char* e = getenv("PFD_GEMM_TRACE");
@@ -1086,34 +1006,12 @@ static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream) {
             "splits=%d grid=%d batched=%d vec=%d plain=%d\n", (long long)p.W * p.H * p.NB, p.N, p.num_kb * BK, p.nseg,
             p.taps[0], p.stride, p.act, p.bias != nullptr, p.residual != nullptr, p.rowadd != nullptr, BN, (int)lean,
             p.splits, grid, p.b_batched, p.vec_ok, (int)(p.cdiv >= p.N));
-  if (!lean) return launch_gemm_t<BN, false, 8>(p, grid, stream);
-  // 16 epilogue warps where the epilogue bounds the tile: per 128 x BN tile the MMA takes ~num_kb * 2 * BN cycles,
-  // the 8-warp epilogue ~3400 (plain) to ~5000 (GEGLU) cycles (r1 ncu source-page measurements)
-  if (g_ew_mode < 0) {          // PFD_GEMM_EW: 8 / 16 force the variant, anything else = automatic
-    const char* e = getenv("PFD_GEMM_EW");
-    g_ew_mode = e ? atoi(e) : 0;
-  }
-  const int ew_mode = g_ew_mode;
-  const long long mma_cycles = (long long)p.num_kb * 2 * BN;
-  const long long epi_cycles = p.act == PFD_ACT_GEGLU ? 5200 : 3400;
-  const bool wide = !stats_ok && (ew_mode == 16 || (ew_mode != 8 && mma_cycles < epi_cycles * 3 / 2));
-  return wide ? launch_gemm_t<BN, true, 16>(p, grid, stream) : launch_gemm_t<BN, true, 8>(p, grid, stream);
+  return lean ? launch_gemm_t<BN, true>(p, grid, stream) : launch_gemm_t<BN, false>(p, grid, stream);
 }
 
 }  // namespace pfd
 
 using namespace pfd;
-
-extern "C" PFD_API int pfd_gemm_stats_written(void) { return g_last_stats; }
-
-extern "C" PFD_API int pfd_set_option(const char* name, int32_t value) {
-  if (name && !strcmp(name, "gemm_epilogue_warps")) {
-    if (value != 0 && value != 8 && value != 16) return set_error("pfd_set_option: gemm_epilogue_warps must be 0, 8 or 16");
-    g_ew_mode = value;
-    return 0;
-  }
-  return set_error("pfd_set_option: unknown option '%s'", name ? name : "(null)");
-}
 
 extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   if (!d) return set_error("pfd_gemm_f16: null descriptor");
@@ -1155,11 +1053,6 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   p.so_c1 = d->so_c1; p.so_c0 = d->so_c0;
   p.ndiv = d->ndiv > 0 ? d->ndiv : 1;
   p.cdiv = d->cdiv > 0 ? d->cdiv : (1 << 30);
-  p.stats = static_cast<float*>(d->stats_out);
-  p.stats_unit = d->stats_unit;
-  if (p.stats && ((reinterpret_cast<uintptr_t>(p.stats) & 7) || d->stats_unit <= 0))
-    return set_error("pfd_gemm_f16: stats_out must be 8-byte aligned with stats_unit > 0");
-  g_last_stats = 0;
   p.vec_ok = (d->so_c0 == 1) && (p.cdiv % 8 == 0) && (d->so_n1 % 8 == 0) && (d->so_n0 % 8 == 0) &&
              (d->so_y % 8 == 0) && (d->so_x % 8 == 0) && (d->so_c1 % 8 == 0) &&
              ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) &&

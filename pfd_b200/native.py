@@ -23,7 +23,7 @@ PFD_MAX_SEG = 3
 ACT_NONE, ACT_SILU, ACT_GELU, ACT_RELU, ACT_GEGLU = 0, 1, 2, 3, 4
 
 EXPORTS = [
-    "pfd_version", "pfd_last_error", "pfd_launch_count", "pfd_gemm_f16", "pfd_gemm_stats_written", "pfd_set_option", "pfd_groupnorm_f16",
+    "pfd_version", "pfd_last_error", "pfd_launch_count", "pfd_set_option", "pfd_gemm_f16", "pfd_groupnorm_f16",
     "pfd_layernorm_f16", "pfd_softmax_f16", "pfd_timestep_embedding_f16", "pfd_upsample2x_f16",
     "pfd_nchw_to_nhwc_f16", "pfd_nhwc_to_nchw_f16", "pfd_im2col3x3_f16", "pfd_axpby_f16",
     "pfd_add_rowvec_f16", "pfd_ddim_step_f16", "pfd_window_gather_f16", "pfd_window_scatter_f16",
@@ -62,8 +62,6 @@ class GemmDesc(ctypes.Structure):
         ("ndiv", c_int32), ("cdiv", c_int32),
         ("bn_force", c_int32),
         ("tap_off", c_int32),
-        ("stats_out", c_void_p),
-        ("stats_unit", c_int32),
         ("stream", c_void_p),
     ]
 
@@ -84,12 +82,10 @@ def load() -> ctypes.CDLL:
     lib.pfd_version.restype = c_int32
     lib.pfd_last_error.restype = c_char_p
     lib.pfd_launch_count.restype = c_int64
+    lib.pfd_set_option.argtypes = [c_char_p, c_int32]
     lib.pfd_gemm_f16.argtypes = [POINTER(GemmDesc)]
     lib.pfd_groupnorm_f16.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int64, c_int32,
-                                      c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
-                                      c_void_p, c_int32, c_void_p]
-    lib.pfd_gemm_stats_written.argtypes = []
-    lib.pfd_set_option.argtypes = [c_char_p, c_int32]
+                                      c_void_p, c_void_p, c_float, c_int32, c_void_p, c_void_p, c_int32, c_void_p]
     lib.pfd_layernorm_f16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_float,
                                       c_void_p, c_void_p]
     lib.pfd_softmax_f16.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int64, c_float, c_void_p,
@@ -143,9 +139,10 @@ def _check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed: {msg.decode() if msg else rc}")
 
 
-def set_option(name: str, value: int) -> None:
-    """Library tuning switch (see pfd_set_option)."""
-    _check(load().pfd_set_option(name.encode(), int(value)), "pfd_set_option")
+def set_env_option(name: Optional[str], value) -> None:
+    """Library tuning switch (pfd_set_option); name=None resets every switch to its default."""
+    _check(load().pfd_set_option(None if name is None else name.encode(), 0 if value is None else int(value)),
+           "pfd_set_option")
 
 
 def stream_ptr() -> int:
@@ -186,10 +183,8 @@ def gemm_raw(segs: Sequence[Tuple[torch.Tensor, int, int, Tuple[int, int, int]]]
              bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None,
              residual: Optional[torch.Tensor] = None, out: torch.Tensor,
              so: Tuple[int, int, int, int, int, int], ndiv: int = 1, cdiv: int = 0,
-             bn_force: int = 0, tap_off: int = 0, stats_unit: int = 0) -> None:
-    """Lowest-level call: ``segs`` is a list of (tensor, taps, channels, (sx, sy, sn)).
-    stats_unit > 0: ask the epilogue for GroupNorm statistics of `out` (per image and unit of that many channels);
-    when the library produced them they are attached to `out` (see `groupnorm`)."""
+             bn_force: int = 0, tap_off: int = 0) -> None:
+    """Lowest-level call: ``segs`` is a list of (tensor, taps, channels, (sx, sy, sn))."""
     d = GemmDesc()
     d.nseg = len(segs)
     for i, (t, taps, c, (sx, sy, sn)) in enumerate(segs):
@@ -213,22 +208,13 @@ def gemm_raw(segs: Sequence[Tuple[torch.Tensor, int, int, Tuple[int, int, int]]]
     d.ndiv, d.cdiv = ndiv, cdiv
     d.bn_force = bn_force
     d.tap_off = tap_off
-    slot = None
-    if stats_unit > 0 and PRODUCER_STATS and act != ACT_GEGLU:
-        slot = _stats_slot(NB * (N // stats_unit) * 8)
-        if slot is not None:
-            d.stats_out, d.stats_unit = slot, stats_unit
     d.stream = stream_ptr()
-    lib = load()
-    _check(lib.pfd_gemm_f16(ctypes.byref(d)), "pfd_gemm_f16")
-    if slot is not None and lib.pfd_gemm_stats_written():
-        out._pfd_stats = (slot, stats_unit, N, NB)
+    _check(load().pfd_gemm_f16(ctypes.byref(d)), "pfd_gemm_f16")
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           alpha: float = 1.0, x2: Optional[torch.Tensor] = None, bn_force: int = 0,
-           stats_unit: int = 0) -> torch.Tensor:
+           alpha: float = 1.0, x2: Optional[torch.Tensor] = None, bn_force: int = 0) -> torch.Tensor:
     """out[M, N] = act(alpha * [x | x2] @ w^T + bias) + residual.  x: [M, K1] (row pitch = stride(0)),
     optional x2: [M, K2]; w: [N, K1+K2] (GEGLU: tile-packed, output has N/2 columns)."""
     M, K1 = x.shape
@@ -241,8 +227,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         segs.append((x2, 1, x2.shape[1], (x2.stride(0), x2.stride(0) * M, x2.stride(0) * M)))
     ldo = out.stride(0)
     gemm_raw(segs, in_w=M, in_h=1, stride=1, W=M, H=1, NB=1, w=w, N=N, K=w.stride(0), alpha=alpha,
-             act=act, bias=bias, residual=residual, out=out, so=(0, 0, 0, ldo, 0, 1), bn_force=bn_force,
-             stats_unit=stats_unit)
+             act=act, bias=bias, residual=residual, out=out, so=(0, 0, 0, ldo, 0, 1), bn_force=bn_force)
     return out
 
 
@@ -273,7 +258,7 @@ def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor]):
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1,
             rowadd: Optional[torch.Tensor] = None, act: int = ACT_NONE,
             residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-            skip: Sequence[torch.Tensor] = (), tap_off: int = 0, stats_unit: int = 0) -> torch.Tensor:
+            skip: Sequence[torch.Tensor] = (), tap_off: int = 0) -> torch.Tensor:
     """3x3 / pad 1 convolution on channel-last x [NB, H, W, C] with packed weights
     w [Cout, 9*C (+ sum of skip channels)] (k = tap*C + c, then the 1x1 skip-segment channels).
     ``skip`` tensors (same raster, stride 1 only) are extra 1x1 K-segments accumulated into the same
@@ -289,22 +274,22 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
         segs.append((s, 1, s.shape[3], (s.stride(2), s.stride(1), s.stride(0))))
     gemm_raw(segs, in_w=W, in_h=H, stride=stride, W=Wo, H=Ho, NB=NB, w=w, N=N, K=w.stride(0), act=act,
              bias=bias, rowadd=rowadd, residual=residual, out=out,
-             so=(out.stride(0), 0, out.stride(1), out.stride(2), 0, 1), tap_off=tap_off, stats_unit=stats_unit)
+             so=(out.stride(0), 0, out.stride(1), out.stride(2), 0, 1), tap_off=tap_off)
     return out
 
 
 def conv1x1(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
             residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-            x2: Optional[torch.Tensor] = None, stats_unit: int = 0) -> torch.Tensor:
+            x2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """1x1 conv on channel-last tensors == linear over flattened pixels."""
     NB, H, W, C = x.shape
     N = w.shape[0]
     if out is None:
         out = torch.empty((NB, H, W, N), device=x.device, dtype=torch.float16)
     r = residual.reshape(NB * H * W, -1) if residual is not None else None
-    o2 = linear(x.reshape(NB * H * W, C), w, bias, act=act, residual=r, out=out.reshape(NB * H * W, N),
-                x2=None if x2 is None else x2.reshape(NB * H * W, -1), stats_unit=stats_unit)
-    return carry_stats(out, o2)
+    linear(x.reshape(NB * H * W, C), w, bias, act=act, residual=r, out=out.reshape(NB * H * W, N),
+           x2=None if x2 is None else x2.reshape(NB * H * W, -1))
+    return out
 
 
 def bmm_nt(a: torch.Tensor, b: torch.Tensor, *, out: torch.Tensor, so, ndiv: int = 1, cdiv: int = 0,
@@ -322,14 +307,10 @@ def bmm_nt(a: torch.Tensor, b: torch.Tensor, *, out: torch.Tensor, so, ndiv: int
 # --------------------------------------------------------------------------------------------
 # GroupNorm statistics scratch: a ring of pre-zeroed slots per (device, stream).  `gn_reset()` zeroes the
 # whole ring with ONE memset (called at the start of every network evaluation); each groupnorm() call then
-# takes the next slot without a memset of its own.  If the ring is exhausted the call zeroes its slot itself.
-# The same ring provides the (pre-zeroed) fp32 slots that GEMM epilogues fill with producer-side statistics.
+# takes the next slot without a memset of its own.  If the ring is exhausted the call zeroes a fallback slot itself.
 _GN_SLOT_BYTES = 64 * 32 * 16 + 256    # up to 64 images x 32 groups x (sum, sumsq) fp64 (+ spare)
-_GN_SLOTS = 384
+_GN_SLOTS = 256
 _gn_rings = {}
-# GroupNorm statistics from the producing GEMM's epilogue (drops the statistics pass of the consumer); PFD_NO_PRODUCER_STATS=1
-# keeps the two-pass GroupNorm everywhere (A/B measurements)
-PRODUCER_STATS = os.environ.get("PFD_NO_PRODUCER_STATS", "0") != "1"
 
 
 def _gn_ring():
@@ -349,58 +330,27 @@ def gn_reset() -> None:
     ring["next"] = 0
 
 
-def _stats_slot(nbytes: int) -> Optional[int]:
-    """Device address of a pre-zeroed ring slot for producer-side statistics, or None (ring exhausted / too large):
-    the consumer then falls back to its own statistics pass."""
-    ring = _gn_ring()
-    if ring["next"] >= _GN_SLOTS or nbytes > _GN_SLOT_BYTES:
-        return None
-    ptr = ring["buf"].data_ptr() + ring["next"] * _GN_SLOT_BYTES
-    ring["next"] += 1
-    return ptr
-
-
-def carry_stats(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
-    """Views (reshape) of a GEMM output keep its producer-side statistics."""
-    st = getattr(src, "_pfd_stats", None)
-    if st is not None:
-        dst._pfd_stats = st
-    return dst
-
-
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, silu: bool,
               x2: Optional[torch.Tensor] = None, groups: int = 32,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(+SiLU) over channel-last x [NB, H, W, C1] (optionally concatenated with x2 [.., C2]).  When every
-    input carries producer-side statistics (`_pfd_stats`, written by the GEMM epilogue that produced it in this
-    network evaluation) with a unit dividing the group size, the statistics pass is skipped."""
+    """GroupNorm(+SiLU) over channel-last x [NB, H, W, C1] (optionally concatenated with x2 [.., C2])."""
     NB, H, W, C1 = x.shape
     C2 = x2.shape[3] if x2 is not None else 0
     if out is None:
         out = torch.empty((NB, H, W, C1 + C2), device=x.device, dtype=torch.float16)
-    s1 = getattr(x, "_pfd_stats", None)
-    s2 = getattr(x2, "_pfd_stats", None) if x2 is not None else None
-    cpg = (C1 + C2) // groups
-    pre = (s1 is not None and s1[2] == C1 and s1[3] == NB and cpg % s1[1] == 0 and
-           (x2 is None or (s2 is not None and s2[1] == s1[1] and s2[2] == C2 and s2[3] == NB)))
-    if pre:
-        _check(load().pfd_groupnorm_f16(x.data_ptr(), C1, _p(x2), C2, NB, H * W, groups, gamma.data_ptr(),
-                                        beta.data_ptr(), eps, int(silu), out.data_ptr(), None, 0, s1[0],
-                                        s2[0] if s2 is not None else None, s1[1], stream_ptr()), "pfd_groupnorm_f16")
-        return out
     ring = _gn_ring()
     need = NB * groups * 16 + NB * 4
     if ring["next"] < _GN_SLOTS and need <= _GN_SLOT_BYTES:
         ws_ptr, zero = ring["buf"].data_ptr() + ring["next"] * _GN_SLOT_BYTES, 0
         ring["next"] += 1
     else:
-        if need > _GN_SLOT_BYTES * _GN_SLOTS:
+        if need > _GN_SLOT_BYTES:
             raise RuntimeError("groupnorm: batch too large for the statistics scratch")
         ws_ptr, zero = ring["buf"].data_ptr() + _GN_SLOTS * _GN_SLOT_BYTES, 1    # shared fallback slot, zeroed per call
         ring["next"] = _GN_SLOTS
     _check(load().pfd_groupnorm_f16(x.data_ptr(), C1, _p(x2), C2, NB, H * W, groups, gamma.data_ptr(),
-                                    beta.data_ptr(), eps, int(silu), out.data_ptr(), ws_ptr, zero, None, None, 0,
-                                    stream_ptr()), "pfd_groupnorm_f16")
+                                    beta.data_ptr(), eps, int(silu), out.data_ptr(), ws_ptr, zero, stream_ptr()),
+           "pfd_groupnorm_f16")
     return out
 
 

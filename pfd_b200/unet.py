@@ -133,30 +133,21 @@ class SpatialTransformer(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # executors
 # ------------------------------------------------------------------------------------------------
-def gn_unit(channels: int) -> int:
-    """Statistics unit the GEMM epilogues emit for tensors that feed GroupNorm(32): channels/32 of the narrowest
-    level.  Every group of every later GroupNorm - including the skip-concat ones, whose group size is
-    (C1 + C2) / 32 - is a whole number of such units (SD-v1.5: 320 / 32 = 10)."""
-    return channels // 32
-
-
-def run_resblock(rb: ResBlock, x: torch.Tensor, x2: Optional[torch.Tensor], emb_out: torch.Tensor,
-                 unit: int = 0) -> torch.Tensor:
+def run_resblock(rb: ResBlock, x: torch.Tensor, x2: Optional[torch.Tensor], emb_out: torch.Tensor) -> torch.Tensor:
     """x (and optional concat partner x2): channel-last [B,H,W,C]; emb_out: [B, Cout] rows (may be a
-    column slice of the batched emb GEMM output).  unit: GroupNorm statistics unit requested from the conv epilogues
-    (the consumers are this block's out_layers norm and the next block's first norm)."""
+    column slice of the batched emb GEMM output)."""
     n0, n1 = rb.in_layers[0], rb.out_layers[0]
     g, b = pk_norm(n0)
     h = nv.groupnorm(x, g, b, n0.eps, silu=True, x2=x2)
     w1, b1 = pk_conv3(rb.in_layers[2])
-    h = nv.conv3x3(h, w1, b1, rowadd=emb_out, stats_unit=unit)
+    h = nv.conv3x3(h, w1, b1, rowadd=emb_out)
     g, b = pk_norm(n1)
     h = nv.groupnorm(h, g, b, n1.eps, silu=True)
     if isinstance(rb.skip_connection, nn.Identity):
         w2, b2 = pk_conv3(rb.out_layers[3])
-        return nv.conv3x3(h, w2, b2, residual=x, stats_unit=unit)
+        return nv.conv3x3(h, w2, b2, residual=x)
     w2, b2 = pk_conv3(rb.out_layers[3], rb.skip_connection)
-    return nv.conv3x3(h, w2, b2, skip=[x] if x2 is None else [x, x2], stats_unit=unit)
+    return nv.conv3x3(h, w2, b2, skip=[x] if x2 is None else [x, x2])
 
 
 def _cat_weights(owner: nn.Module, key: str, lins) -> torch.Tensor:
@@ -178,7 +169,7 @@ def context_kv(st: SpatialTransformer, context: torch.Tensor) -> Tuple[torch.Ten
 
 
 def run_spatial_transformer(st: SpatialTransformer, x: torch.Tensor, context: torch.Tensor,
-                            kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, unit: int = 0) -> torch.Tensor:
+                            kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
     B, H, W, C = x.shape
     N = H * W
     heads, d = st.n_heads, st.d_head
@@ -226,8 +217,8 @@ def run_spatial_transformer(st: SpatialTransformer, x: torch.Tensor, context: to
     t = nv.linear(gg, w, bb, residual=t)
     # --- proj_out + residual with the block input (attention.py:368-371)
     w, bb = pk_lin(st.proj_out)
-    out = nv.linear(t, w, bb, residual=x.reshape(B * N, C), stats_unit=unit)
-    return nv.carry_stats(out.reshape(B, H, W, C), out)
+    out = nv.linear(t, w, bb, residual=x.reshape(B * N, C))
+    return out.reshape(B, H, W, C)
 
 
 def time_embed_silu(time_embed: IndexedSequential, t: torch.Tensor, model_channels: int) -> torch.Tensor:
@@ -350,16 +341,15 @@ class UNetModel2D_Next(nn.Module):
 
     def run_data_block(self, idx: int, h, h2, embs: Dict[int, torch.Tensor]):
         layer = self.data_blocks[idx][0]
-        unit = gn_unit(self.model_channels)
         if isinstance(layer, ResBlock):
-            return run_resblock(layer, h, h2, embs[idx], unit)
+            return run_resblock(layer, h, h2, embs[idx])
         assert h2 is None
         if isinstance(layer, Downsample):
             w, b = pk_conv3(layer.op)
-            return nv.conv3x3(h, w, b, stride=2, stats_unit=unit)
+            return nv.conv3x3(h, w, b, stride=2)
         if isinstance(layer, Upsample):
             w, b = pk_conv3(layer.conv)
-            return nv.conv3x3(nv.upsample2x(h), w, b, stats_unit=unit)
+            return nv.conv3x3(nv.upsample2x(h), w, b)
         if isinstance(layer, IndexedSequential):                      # GN, SiLU, conv (openaimodel.py:2732)
             g, b = pk_norm(layer[0])
             hn = nv.groupnorm(h, g, b, layer[0].eps, silu=True)
@@ -369,8 +359,7 @@ class UNetModel2D_Next(nn.Module):
             w, b, kpad = pk_conv3_small(layer)
             B, H, W, _ = h.shape
             col = nv.im2col3x3(h, kpad)
-            o = nv.linear(col.reshape(B * H * W, kpad), w, b, stats_unit=unit)
-            return nv.carry_stats(o.reshape(B, H, W, w.shape[0]), o)
+            return nv.linear(col.reshape(B * H * W, kpad), w, b).reshape(B, H, W, w.shape[0])
         raise RuntimeError(f"unknown data block {type(layer)}")
 
     def apply(self, x: torch.Tensor, timesteps: torch.Tensor, context: torch.Tensor,
@@ -404,7 +393,7 @@ class UNetModel2D_Next(nn.Module):
             elif lt == 'c':
                 st = self.context_blocks[ci][0]
                 if mixed_contexts is None:
-                    h = run_spatial_transformer(st, h, context, kv[ci], gn_unit(self.model_channels))
+                    h = run_spatial_transformer(st, h, context, kv[ci])
                 else:                                                    # pfd.py:374-379 context_mixing
                     acc = None
                     for cm, r in mixed_contexts:

@@ -35,8 +35,8 @@ def test_gemm_desc_layout_matches_header():
     from pfd_b200 import native
     d = native.GemmDesc()
     # 1+3+3 int32 (=28, pad to 32) + 3 ptr + 9 int64 + 6 int32 + ptr + int32(+pad) + 2 int64 + float + int32
-    # + 4 ptr + 6 int64 + 4 int32 (ndiv, cdiv, bn_force, tap_off) + stats_out ptr + stats_unit int32 (+pad) + stream ptr
-    assert ctypes.sizeof(d) == 32 + 24 + 72 + 24 + 8 + 8 + 16 + 8 + 40 + 48 + 16 + 8 + 8 + 8
+    # + 4 ptr + 6 int64 + 4 int32 (ndiv, cdiv, bn_force, tap_off) + stream ptr
+    assert ctypes.sizeof(d) == 32 + 24 + 72 + 24 + 8 + 8 + 16 + 8 + 40 + 48 + 16 + 8
     # and the same field order as the header declares
     import re
     src = open(os.path.join(ROOT, "include", "pfd_b200.h")).read()

@@ -315,60 +315,3 @@ def test_flash_attention_fused_qk_swapped_vt(nv, B, heads, N, d):
     sc = (torch.matmul(qf, kf.transpose(-1, -2)).half().float() * scale).half().float()
     ref = torch.matmul(torch.softmax(sc, -1), vf).permute(0, 2, 1, 3).reshape(B, N, C)
     close(o, ref, rtol=8e-3, atol=4e-3)
-
-
-@pytest.mark.parametrize("NB,H,W,C,N,unit,res", [(2, 64, 64, 320, 320, 10, True), (8, 8, 8, 640, 1280, 10, False),
-                                                (2, 32, 32, 128, 256, 4, True), (3, 16, 16, 320, 640, 10, False),
-                                                (1, 24, 40, 64, 128, 4, False)])
-def test_groupnorm_statistics_from_the_producer_epilogue(nv, NB, H, W, C, N, unit, res):
-    """conv3x3 with stats_unit: the epilogue accumulates per-(image, unit) sum / sumsq of its fp16 outputs; the
-    consuming GroupNorm then skips its statistics pass.  Must equal the two-pass GroupNorm of the same tensor."""
-    x = rnd(NB, H, W, C)
-    w = rnd(N, 9 * C, scale=(9 * C) ** -0.5, seed=1)
-    b = rnd(N, seed=2)
-    r = rnd(NB, H, W, N, seed=3) if res else None
-    gamma, beta = rnd(N, seed=4) + 1.0, rnd(N, seed=5)
-    nv.gn_reset()
-    y = nv.conv3x3(x, w, b, residual=r, stats_unit=unit)
-    y_plain = nv.conv3x3(x, w, b, residual=r)
-    assert torch.equal(y, y_plain)                                       # statistics do not change the output
-    if NB * H * W >= 8192:                                               # (few tiles + long K -> split-K path -> consumer-side statistics)
-        assert getattr(y, "_pfd_stats", None) is not None
-    out_pre = nv.groupnorm(y, gamma, beta, 1e-5, silu=True)
-    out_two = nv.groupnorm(y_plain, gamma, beta, 1e-5, silu=True)
-    torch.cuda.synchronize()
-    ref = F.silu(F.group_norm(y.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-5)).permute(0, 2, 3, 1)
-    close(out_two, ref, rtol=6e-3, atol=6e-3)
-    close(out_pre, ref, rtol=6e-3, atol=6e-3)
-    if getattr(y, "_pfd_stats", None) is not None:
-        # the statistics themselves: fp32 sums of the fp16 outputs per (image, unit)
-        slot, u, n_ch, nb = y._pfd_stats
-        assert (u, n_ch, nb) == (unit, N, NB)
-        yf = y.float().reshape(NB, H * W, N // unit, unit)
-        s_ref, q_ref = yf.sum((1, 3)), yf.pow(2).sum((1, 3))
-        st = _peek(slot, NB * (N // unit) * 2).reshape(NB, N // unit, 2)
-        close(st[..., 0], s_ref, rtol=2e-3, atol=2e-1)
-        close(st[..., 1], q_ref, rtol=2e-3, atol=2e-1)
-
-
-def _peek(ptr, n):
-    """Read n fp32 values at a raw device address (inside the statistics ring of native.py)."""
-    from pfd_b200 import native
-    ring = native._gn_ring()
-    off = ptr - ring["buf"].data_ptr()
-    return ring["buf"][off:off + 4 * n].view(torch.float32).clone()
-
-
-def test_groupnorm_concat_with_producer_statistics(nv):
-    """Skip-concat GroupNorm (group size 60 = six 10-channel units, groups straddling the two sources)."""
-    NB, H, W = 2, 64, 64
-    xa, xb = rnd(NB, H, W, 320), rnd(NB, H, W, 320, seed=7)
-    wa, wb = rnd(1280, 9 * 320, scale=0.02, seed=1), rnd(640, 9 * 320, scale=0.02, seed=2)
-    nv.gn_reset()
-    a = nv.conv3x3(xa, wa, None, stats_unit=10)
-    b = nv.conv3x3(xb, wb, None, stats_unit=10)
-    assert getattr(a, "_pfd_stats", None) is not None and getattr(b, "_pfd_stats", None) is not None
-    gamma, beta = rnd(1920, seed=4) + 1.0, rnd(1920, seed=5)
-    out = nv.groupnorm(a, gamma, beta, 1e-5, silu=False, x2=b)
-    ref = F.group_norm(torch.cat([a, b], 3).float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-5)
-    close(out, ref.permute(0, 2, 3, 1), rtol=6e-3, atol=6e-3)

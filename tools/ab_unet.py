@@ -2,8 +2,10 @@
 settings INSIDE ONE PROCESS, interleaved, so that box-to-box spread and the power/thermal state do not bias the
 comparison (r2: three separate bench.py runs on one box disagreed by 4 % in the opposite direction of their own
 per-kernel breakdowns).  Each variant is captured into its own CUDA graph; rounds alternate between the graphs.
+profiles/r2_ab_unet_ew16_producer_stats.log is the run that rejected the 16-epilogue-warp GEMM variant and the
+producer-side GroupNorm statistics (both removed again).
 
-    python tools/ab_unet.py [--rounds 6] [--reps 20] [--control]
+    python tools/ab_unet.py [--rounds 6] [--reps 20] [--control] [--env-variant name=option:value ...]
 """
 import argparse
 import json
@@ -23,6 +25,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--control", action="store_true")
+    ap.add_argument("--env-variant", action="append", default=[],
+                    help="name=OPTION:value - an extra variant that sets a library option (pfd_set_option) before capture")
     args = ap.parse_args()
     from pfd_b200 import get_model, model_cfg_bank, native as nv
     from pfd_b200.weights import SCHEDULE_BUFFERS, fill_module_
@@ -45,25 +49,23 @@ def main():
     def run():
         return net.apply_model({"type": "image", "x": torch.cat([x, x])}, t_in, c_info)
 
-    variants = {
-        "default (EW auto, producer GN stats)": dict(ew=0, stats=True),
-        "EW=8 everywhere, producer stats": dict(ew=8, stats=True),
-        "EW auto, two-pass GroupNorm": dict(ew=0, stats=False),
-        "EW=8, two-pass GroupNorm (r1 behaviour)": dict(ew=8, stats=False),
-        "EW=16 forced, two-pass GroupNorm": dict(ew=16, stats=False),
-    }
+    # name -> callable applied before that variant's warm-up + capture (library switches, python-level toggles ...)
+    variants = {"default": lambda: None}
+    for spec in args.env_variant:                      # e.g. --env-variant flash_poly=PFD_FLASH_POLY:1
+        vname, kv = spec.split("=", 1)
+        key, val = kv.split(":", 1)
+        variants[vname] = (lambda k=key, v=val: nv.set_env_option(k, v))
     graphs = {}
-    for name, v in variants.items():
-        nv.set_option("gemm_epilogue_warps", v["ew"])
-        nv.PRODUCER_STATS = v["stats"]
+    for name, setup in variants.items():
+        nv.set_env_option(None, None)                  # back to the defaults
+        setup()
         run()
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
             out = run()
         graphs[name] = (gr, out)
-    nv.set_option("gemm_epilogue_warps", 0)
-    nv.PRODUCER_STATS = True
+    nv.set_env_option(None, None)
     ref = None
     times = {k: [] for k in graphs}
     for gr, _ in graphs.values():
