@@ -30,6 +30,7 @@ namespace pfd {
 constexpr int FA_BQ = 128;
 constexpr int FA_BKV = 64;
 constexpr int FA_THREADS = 192;
+constexpr int FLASH_POLY_MOD_DEFAULT = 0;
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
@@ -45,6 +46,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^t for two logits on the FMA / ALU pipes in packed half2 (the softmax of the d = 40 level is bound by the MUFU pipe:
+// 16 ex2 per clock per SM against 4 * d MMA flops per exponential): Cody-Waite split t = n + f with n = round(t) taken
+// from the mantissa of t + 1536 (ulp 1 in that binade), 2^f on [-0.5, 0.5] by a degree-3 polynomial in fp16 Horner
+// form (max rel. error 7e-4, rms 2.5e-4: the size of the fp16 rounding P gets anyway; tools/fit_exp2.py), and 2^n built
+// from the same mantissa bits as a half whose exponent field is n + 15 (t < -15 -> +0.0, like the flushed MUFU path).
+// 12 issue slots per pair instead of 2 MUFU + 1 F2FP.  Valid for t <= 15.
+__device__ __forceinline__ uint32_t exp2_poly_h2(float t0, float t1) {
+  const __half2 lo = __floats2half2_rn(-15.f, -15.f), magic = __floats2half2_rn(1536.f, 1536.f);
+  const __half2 c3 = __floats2half2_rn(0.05592204f, 0.05592204f), c2 = __floats2half2_rn(0.24264008f, 0.24264008f);
+  const __half2 c1 = __floats2half2_rn(0.69312103f, 0.69312103f), c0 = __floats2half2_rn(0.99992448f, 0.99992448f);
+  const __half2 h = __hmax2(__floats2half2_rn(t0, t1), lo);
+  const __half2 r = __hadd2(h, magic);
+  const __half2 f = __hsub2(h, __hsub2(r, magic));
+  __half2 pz = __hfma2(c3, f, c2);
+  pz = __hfma2(pz, f, c1);
+  pz = __hfma2(pz, f, c0);
+  const uint32_t rb = *reinterpret_cast<const uint32_t*>(&r);
+  const uint32_t sb = ((rb & 0x03ff03ffu) - 0x01f101f1u) << 10;
+  const __half2 o = __hmul2(pz, *reinterpret_cast<const __half2*>(&sb));
+  return *reinterpret_cast<const uint32_t*>(&o);
 }
 
 struct alignas(64) FlashParams {
@@ -78,7 +101,8 @@ struct FlashCfg {
   static int smem_bytes(int dN) { return Q_BYTES + NKV * K_BYTES + NVS * dN * 128 + NPB * P_BYTES + 1024 + 128; }
 };
 
-template <int DCH>
+// PM > 0: every PM-th pair of exponentials of a key block takes the polynomial path (exp2_poly_h2) instead of MUFU
+template <int DCH, int PM>
 __global__ void __launch_bounds__(FA_THREADS, FlashCfg<DCH>::MIN_CTAS)
 flash_attn_kernel(const __grid_constant__ FlashParams p) {
   using Cfg = FlashCfg<DCH>;
@@ -289,10 +313,14 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       uint32_t pk[FA_BKV / 2];
 #pragma unroll
       for (int i = 0; i < FA_BKV / 2; ++i) {
-        const float e0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), c2, nm));
-        const float e1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), c2, nm));
-        const __half2 h = __floats2half2_rn(e0, e1);
-        pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        const float t0 = fmaf(__uint_as_float(r[2 * i]), c2, nm);
+        const float t1 = fmaf(__uint_as_float(r[2 * i + 1]), c2, nm);
+        if (PM > 0 && (i % (PM > 0 ? PM : 1)) == (PM > 0 ? PM : 1) - 1) {
+          pk[i] = exp2_poly_h2(t0, t1);
+        } else {
+          const __half2 h = __floats2half2_rn(fast_exp2(t0), fast_exp2(t1));
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
       }
       if (j > 0) {
         // single P buffer / running O: PV_{j-1} must have consumed P and finished accumulating
@@ -391,18 +419,18 @@ static int encode4d(CUtensorMap* m, const void* ptr, cuuint64_t inner, cuuint64_
   return 0;
 }
 
-template <int DCH>
+template <int DCH, int PM>
 static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t st) {
   using Cfg = FlashCfg<DCH>;
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DCH, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::smem_bytes(Cfg::DN));
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(flash DCH=%d): %s", DCH, cudaGetErrorString(e));
     done = true;
   }
   const int smem = Cfg::smem_bytes((p.d + 16) & ~15);
-  launch_k(flash_attn_kernel<DCH>, grid, dim3(FA_THREADS), (size_t)smem, st, p);
+  launch_k(flash_attn_kernel<DCH, PM>, grid, dim3(FA_THREADS), (size_t)smem, st, p);
   return check_launch("pfd_flash_attn_f16");
 }
 
@@ -433,9 +461,16 @@ extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, 
   p.o_sb = o_sb; p.o_sq = o_sq; p.o_sh = d;
   dim3 grid((Nq + FA_BQ - 1) / FA_BQ, (unsigned)((long long)B * heads));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (d <= 64) return launch_flash<1>(p, grid, st);
-  if (d <= 128) return launch_flash<2>(p, grid, st);
-  return launch_flash<3>(p, grid, st);
+  if (d <= 64) {
+    // d <= 64 is MUFU-bound: a share of the exponentials goes to the FMA pipe ("flash_poly_mod": every n-th pair)
+    const int pm = option("flash_poly_mod", FLASH_POLY_MOD_DEFAULT);
+    if (pm == 2) return launch_flash<1, 2>(p, grid, st);
+    if (pm == 3) return launch_flash<1, 3>(p, grid, st);
+    if (pm == 4) return launch_flash<1, 4>(p, grid, st);
+    return launch_flash<1, 0>(p, grid, st);
+  }
+  if (d <= 128) return launch_flash<2, 0>(p, grid, st);
+  return launch_flash<3, 0>(p, grid, st);
 }
 
 extern "C" PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const void* vt, void* out, int32_t B,

@@ -315,3 +315,39 @@ def test_flash_attention_fused_qk_swapped_vt(nv, B, heads, N, d):
     sc = (torch.matmul(qf, kf.transpose(-1, -2)).half().float() * scale).half().float()
     ref = torch.matmul(torch.softmax(sc, -1), vf).permute(0, 2, 1, 3).reshape(B, N, C)
     close(o, ref, rtol=8e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("pm", [2, 3, 4])
+@pytest.mark.parametrize("B,heads,Nq,Nk,d,qscale", [(2, 8, 4096, 4096, 40, 1.0), (2, 8, 1024, 148, 40, 1.0),
+                                                   (1, 4, 300, 200, 64, 4.0), (1, 2, 128, 77, 8, 1.0)])
+def test_flash_attention_polynomial_exp2(nv, pm, B, heads, Nq, Nk, d, qscale):
+    """flash_poly_mod = n: every n-th pair of exponentials is computed on the FMA pipe (packed-half2 Cody-Waite +
+    degree-3 polynomial) instead of MUFU.  Same tolerance as the MUFU path; qscale = 4 makes peaked rows (logit
+    range ~ +-30: exercises the 2^n scaling, the t < -15 flush and the lazy-rescale headroom)."""
+    g = torch.Generator().manual_seed(pm * 100 + Nq)
+    q = (qscale * torch.randn((B * heads, Nq, d), generator=g)).cuda().half()
+    Nkp = (Nk + 7) // 8 * 8
+    k = torch.zeros((B * heads, Nkp, d), device="cuda", dtype=torch.float16)
+    k[:, :Nk] = torch.randn((B * heads, Nk, d), generator=g).cuda().half()
+    vt = torch.zeros((B * heads, d, Nkp), device="cuda", dtype=torch.float16)
+    vt[:, :, :Nk] = torch.randn((B * heads, d, Nk), generator=g).cuda().half()
+    scale = d ** -0.5
+    out0 = torch.empty((B, Nq, heads * d), device="cuda", dtype=torch.float16)
+    out1 = torch.empty_like(out0)
+    nv.set_env_option(None, None)
+    nv.flash_attn(q, k, vt, B=B, heads=heads, Nq=Nq, Nk=Nk, scale=scale, out=out0)
+    try:
+        nv.set_env_option("flash_poly_mod", pm)
+        nv.flash_attn(q, k, vt, B=B, heads=heads, Nq=Nq, Nk=Nk, scale=scale, out=out1)
+    finally:
+        nv.set_env_option(None, None)
+    torch.cuda.synchronize()
+    s = (torch.bmm(q.float(), k[:, :Nk].float().transpose(1, 2)).half().float() * scale).half().float()
+    ref = torch.bmm(torch.softmax(s, -1), vt[:, :, :Nk].float().transpose(1, 2))
+    ref = ref.reshape(B, heads, Nq, d).permute(0, 2, 1, 3).reshape(B, Nq, heads * d)
+    close(out0, ref, rtol=8e-3, atol=4e-3)
+    close(out1, ref, rtol=8e-3, atol=4e-3)
+    e0 = ((out0.float() - ref).pow(2).mean() / ref.pow(2).mean()).sqrt().item()
+    e1 = ((out1.float() - ref).pow(2).mean() / ref.pow(2).mean()).sqrt().item()
+    print(f"[flash poly] pm={pm} N={Nq}x{Nk} d={d}: rel rms MUFU {e0:.2e}  poly {e1:.2e}")
+    assert e1 < max(2.0 * e0, 1.5e-3)
