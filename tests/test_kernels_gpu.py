@@ -342,7 +342,13 @@ def test_flash_attention_polynomial_exp2(nv, pm, B, heads, Nq, Nk, d, qscale):
     finally:
         nv.set_env_option(None, None)
     torch.cuda.synchronize()
-    s = (torch.bmm(q.float(), k[:, :Nk].float().transpose(1, 2)).half().float() * scale).half().float()
+    s = torch.bmm(q.float(), k[:, :Nk].float().transpose(1, 2))
+    if qscale == 1.0:
+        s = (s.half().float() * scale).half().float()      # the reference's fp16 score tensor (attention.py:188)
+    else:
+        # peaked rows (|logit| ~ 30): an fp16 score tensor carries 1.6e-2 absolute logit error, i.e. percent-level
+        # noise in P that is the REFERENCE's rounding, not the kernel's (fp32 logits) -> compare with exact logits
+        s = s * scale
     ref = torch.bmm(torch.softmax(s, -1), vt[:, :, :Nk].float().transpose(1, 2))
     ref = ref.reshape(B, heads, Nq, d).permute(0, 2, 1, 3).reshape(B, Nq, heads * d)
     close(out0, ref, rtol=8e-3, atol=4e-3)
