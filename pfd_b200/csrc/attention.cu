@@ -389,6 +389,306 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Short-key attention: the UNet / ControlNet CROSS-attention against the 148 SeeCoder context tokens
+// (attention.py:178-201 with `context`; Nk = 148 at every level, d = 40 at the 64x64 level where 94 % of its
+// exponentials are).  All keys fit ONE score tile, so there is no online softmax: S = Q K^T is a single
+// 128 x 160 tcgen05.mma tile, the row maximum is exact, P is written once and O = P V^T is 10 k-steps.
+// The generic kernel above spends most of such a launch in per-CTA set-up (TMEM allocation, barrier init, cold Q
+// load: 3 key blocks per CTA, the third one 69 % padding); this one is PERSISTENT: each CTA walks a contiguous
+// range of (batch*head, query tile) items, K / V^T of a head stay in shared memory until the head changes, and
+// two softmax groups (8 warps each, two threads per query row) alternate items on private S / O accumulators and P
+// buffers so one group's MUFU phase
+// overlaps the other's TMEM loads, shared-memory stores and output epilogue.
+//   warp 0      : TMA producer (Q tile per item through a 2-slot ring; K + V^T per head through a 2-slot ring)
+//   warp 1      : tcgen05.mma issuer: S(0) S(1) [PV(i) S(i+2)]...
+//   warps 2..9  : softmax / epilogue group 0 (even items), warps 10..17: group 1 (odd items); warps wi and wi + 4
+//                 of a group share the query rows of a TMEM lane quarter and split the score columns 80 / 80
+// Barrier protocol (single arrival unless noted): q_full/q_empty[2], kv_full/kv_empty[2], s_full[2],
+// p_ready[2] (256 arrivals), o_full[2].  There is no s_free / o_free barrier: group g arrives on p_ready only
+// after it has read S_g completely and (one item earlier) drained O_g, and the issuer orders S(i+2) and PV(i+2)
+// behind the wait on p_ready(i) / p_ready(i+2).
+constexpr int XS_NKP = 160;        // score tile width (keys, padded to the UMMA N granule of 16)
+constexpr int XS_THREADS = 64 + 2 * 256;   // TMA warp, MMA warp, 2 softmax groups of 8 warps
+constexpr int XS_Q_BYTES = FA_BQ * 128;
+constexpr int XS_K_BYTES = XS_NKP * 128;
+constexpr int XS_P_BYTES = 3 * FA_BQ * 128;      // 3 chunks of 64 keys (the third one half used)
+
+struct alignas(64) XsParams {
+  CUtensorMap tmQ, tmK, tmV;
+  int Nq, Nk, heads, d;
+  int nqt, total;                  // query tiles per (batch, head); work items = B * heads * nqt
+  float scale;
+  __half* out;
+  long long o_sb, o_sq, o_sh;
+};
+
+static int xs_smem_bytes(int dN) { return 2 * XS_Q_BYTES + 2 * XS_K_BYTES + 2 * 3 * dN * 128 + 2 * XS_P_BYTES + 1024 + 256 + 2048; }
+
+template <int PM>
+__global__ void __launch_bounds__(XS_THREADS, 1)
+xattn_short_kernel(const __grid_constant__ XsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const int d = p.d;
+  const int dN = (d + 16) & ~15;                 // value rows + the all-ones row (row sums), padded to 16
+  const int VC_BYTES = dN * 128;                 // one 64-key chunk of V^T
+  const int V_BYTES = 3 * VC_BYTES;
+  const uint32_t sQ = base;                      // [2][XS_Q_BYTES]
+  const uint32_t sK = sQ + 2 * XS_Q_BYTES;       // [2][XS_K_BYTES]
+  const uint32_t sV = sK + 2 * XS_K_BYTES;       // [2][3][VC_BYTES]
+  const uint32_t sP = sV + 2 * V_BYTES;          // [2][XS_P_BYTES]
+  const uint32_t bars = sP + 2 * XS_P_BYTES;
+  const int off_V = 2 * XS_Q_BYTES + 2 * XS_K_BYTES;
+  const int off_P = off_V + 2 * V_BYTES;
+  const int off_bars = off_P + 2 * XS_P_BYTES;
+  const int off_mx = off_bars + 256;             // [2 groups][2 halves][128] fp32 partial row maxima
+  auto q_full = [&](int s) { return bars + 8u * (0 + s); };
+  auto q_empty = [&](int s) { return bars + 8u * (2 + s); };
+  auto kv_full = [&](int s) { return bars + 8u * (4 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (6 + s); };
+  auto s_full = [&](int s) { return bars + 8u * (8 + s); };
+  auto p_ready = [&](int s) { return bars + 8u * (10 + s); };
+  auto o_full = [&](int s) { return bars + 8u * (12 + s); };
+  const uint32_t tmem_slot = bars + 8u * 14;
+  volatile uint32_t* tmem_slot_g = reinterpret_cast<volatile uint32_t*>(gbase + off_bars + 8 * 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // contiguous, balanced range of work items for this CTA
+  const int lo = (int)(((long long)p.total * blockIdx.x) / gridDim.x);
+  const int hi = (int)(((long long)p.total * (blockIdx.x + 1)) / gridDim.x);
+  const int n = hi - lo;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(p_ready(s), 256);
+      mbar_init(o_full(s), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_rt(tmem_slot, 512u);
+  if (warp >= 2) {
+    // rows d..dN-1 of every V^T chunk are never written by TMA (its box has d rows): row d = ones, rest = 0
+    const int t = threadIdx.x - 64;
+    const int per_chunk = (dN - d) * 8;              // 16-byte granules
+    for (int i = t; i < 6 * per_chunk; i += XS_THREADS - 64) {
+      const int ch = i / per_chunk, g = i % per_chunk;
+      const uint32_t word = (g < 8) ? 0x3C003C00u : 0u;
+      *reinterpret_cast<uint4*>(gbase + off_V + ch * VC_BYTES + d * 128 + g * 16) = make_uint4(word, word, word, word);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  auto tS = [&](int g) { return tmem_base + (uint32_t)(g * XS_NKP); };
+  auto tO = [&](int g) { return tmem_base + (uint32_t)(2 * XS_NKP + g * dN); };
+  pdl_wait();                  // q is produced by the preceding projection GEMM
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int kvn = -1, prev_bh = -1;
+      for (int li = 0; li < n; ++li) {
+        const int item = lo + li;
+        const int bh = item / p.nqt, qt = item % p.nqt;
+        const int hb = bh % p.heads, bb = bh / p.heads;
+        if (bh != prev_bh) {
+          ++kvn;
+          prev_bh = bh;
+          const int ks = kvn & 1, ku = kvn >> 1;
+          if (ku >= 1) mbar_wait(kv_empty(ks), (ku - 1) & 1);     // every MMA that read the slot has completed
+          const int nvc = (p.Nk + 63) >> 6;                       // 64-key chunks of V^T that hold valid keys
+          mbar_expect_tx(kv_full(ks), XS_K_BYTES + nvc * d * 128);
+          tma_load_4d(sK + ks * XS_K_BYTES, &p.tmK, kv_full(ks), 0, 0, hb, bb);
+          for (int c = 0; c < nvc; ++c)
+            tma_load_4d(sV + ks * V_BYTES + c * VC_BYTES, &p.tmV, kv_full(ks), c * 64, 0, hb, bb);
+        }
+        const int qs = li & 1, qu = li >> 1;
+        if (qu >= 1) mbar_wait(q_empty(qs), (qu - 1) & 1);        // S of item li - 2 has read the slot
+        mbar_expect_tx(q_full(qs), XS_Q_BYTES);
+        tma_load_4d(sQ + qs * XS_Q_BYTES, &p.tmQ, q_full(qs), 0, qt * FA_BQ, hb, bb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(XS_NKP);
+      const uint32_t idesc_o = make_idesc_f16((uint32_t)dN);
+      const int ksteps_s = (d + 15) / 16;
+      const int ksteps_o = (p.Nk + 15) / 16;
+      int s_kvn = -1, s_prev = -1, o_kvn = -1, o_prev = -1;
+      auto issue_S = [&](int li) {
+        const int bh = (lo + li) / p.nqt;
+        if (bh != s_prev) {
+          ++s_kvn;
+          s_prev = bh;
+        }
+        const int g = li & 1, u = li >> 1;
+        mbar_wait(q_full(g), u & 1);
+        mbar_wait(kv_full(s_kvn & 1), (s_kvn >> 1) & 1);
+        tc_fence_after();
+        const uint64_t ad = make_sw128_kmajor_desc(sQ + g * XS_Q_BYTES);
+        const uint64_t bd = make_sw128_kmajor_desc(sK + (s_kvn & 1) * XS_K_BYTES);
+        for (int s = 0; s < ksteps_s; ++s) umma_f16(tS(g), ad + 2u * s, bd + 2u * s, idesc_s, s > 0 ? 1u : 0u);
+        umma_commit(s_full(g));
+        umma_commit(q_empty(g));
+      };
+      auto issue_PV = [&](int li) {
+        const int bh = (lo + li) / p.nqt;
+        if (bh != o_prev) {
+          ++o_kvn;
+          o_prev = bh;
+        }
+        const int g = li & 1, u = li >> 1;
+        mbar_wait(p_ready(g), u & 1);
+        tc_fence_after();
+        for (int s = 0; s < ksteps_o; ++s) {
+          const int c = s >> 2, k4 = s & 3;
+          const uint64_t ad = make_sw128_kmajor_desc(sP + g * XS_P_BYTES + c * (FA_BQ * 128));
+          const uint64_t bd = make_sw128_kmajor_desc(sV + (o_kvn & 1) * V_BYTES + c * VC_BYTES);
+          umma_f16(tO(g), ad + 2u * k4, bd + 2u * k4, idesc_o, s > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full(g));
+        const bool last_of_head = (li + 1 == n) || ((lo + li + 1) / p.nqt != bh);
+        if (last_of_head) umma_commit(kv_empty(o_kvn & 1));
+      };
+      if (n > 0) issue_S(0);
+      if (n > 1) issue_S(1);
+      for (int li = 0; li < n; ++li) {
+        issue_PV(li);
+        if (li + 2 < n) issue_S(li + 2);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / output groups (8 warps each)
+    // Two threads per query row: warps wi and wi + 4 of a group read the same TMEM lanes, thread `half` owns score
+    // columns [80 half, 80 half + 80) -> all of its logits sit in registers after ONE round of tcgen05.ld (no second
+    // pass over TMEM), 80 exponentials per thread per item, and 4 softmax warps per scheduler keep the MUFU pipe fed.
+    // The row maximum is exchanged through shared memory under a 256-thread named barrier.
+    const int g = (warp - 2) >> 3;
+    const int half = ((warp - 2) & 7) >> 2;
+    const int qd = warp & 3;                           // TMEM lane quarter this warp may access
+    const int row = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const float c2 = p.scale * 1.4426950408889634f;    // logits in log2 units
+    uint8_t* prow = gbase + off_P + g * XS_P_BYTES + row * 128;
+    const int rsw = row & 7;
+    const int cb = half * 80;                          // first score column of this thread
+    const int nvalid = min(max(p.Nk - cb, 0), 80);     // valid keys among its 80 columns
+    const int kcols = ((p.Nk + 15) >> 4) << 4;         // P columns the PV MMA reads
+    float* mxs = reinterpret_cast<float*>(gbase + off_mx) + g * 256;     // [half][row] partial row maxima
+    const uint32_t tSg = tS(g) + lane_off + cb, tOg = tO(g) + lane_off;
+    for (int li = g; li < n; li += 2) {
+      const int u = li >> 1;
+      const int item = lo + li;
+      const int bh = item / p.nqt, qt = item % p.nqt;
+      mbar_wait(s_full(g), u & 1);
+      tc_fence_after();
+      uint32_t r[80];
+      tmem_ld32(tSg, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld32(tSg + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      tmem_ld16(tSg + 64, *reinterpret_cast<uint32_t(*)[16]>(&r[64]));
+      tmem_ld_wait();
+      if (nvalid < 80) {
+#pragma unroll
+        for (int i = 0; i < 80; ++i)
+          if (i >= nvalid) r[i] = 0xff800000u;          // -inf: masked keys contribute exp2(-inf) = 0
+      }
+      // exact row maximum: local (five independent 3-input max chains), then exchanged with the partner thread
+      float mx[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        mx[q] = fmax3(__uint_as_float(r[q * 16]), __uint_as_float(r[q * 16 + 1]), __uint_as_float(r[q * 16 + 2]));
+#pragma unroll
+        for (int i = 3; i + 1 < 16; i += 2)
+          mx[q] = fmax3(mx[q], __uint_as_float(r[q * 16 + i]), __uint_as_float(r[q * 16 + i + 1]));
+        mx[q] = fmaxf(mx[q], __uint_as_float(r[q * 16 + 15]));
+      }
+      const float mloc = fmax3(fmax3(mx[0], mx[1], mx[2]), mx[3], mx[4]);
+      mxs[half * 128 + row] = mloc;
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float mrow = fmaxf(mloc, mxs[(half ^ 1) * 128 + row]);
+      const float nm = -mrow * c2;
+      // p = 2^(s * c2 - m) -> fp16 P in the K-major 128B-swizzled layout the PV MMA reads, 8 columns per granule
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float t0 = fmaf(__uint_as_float(r[8 * j + 2 * i]), c2, nm);
+          const float t1 = fmaf(__uint_as_float(r[8 * j + 2 * i + 1]), c2, nm);
+          if (PM > 0 && ((4 * j + i) % (PM > 0 ? PM : 1)) == (PM > 0 ? PM : 1) - 1) {
+            pk[i] = exp2_poly_h2(t0, t1);
+          } else {
+            const __half2 h = __floats2half2_rn(fast_exp2(t0), fast_exp2(t1));
+            pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        }
+        const int gc = cb + 8 * j;                      // first score column of this granule
+        if (gc < kcols)
+          *reinterpret_cast<uint4*>(prow + (gc >> 6) * (FA_BQ * 128) + ((((gc & 63) >> 3) ^ rsw) << 4)) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready(g));
+      // ---- epilogue of this item: O / l -> [B, Nq, heads*d]   (l = column d of the accumulator); the two threads
+      //      of a row take alternate 16-column chunks of O
+      mbar_wait(o_full(g), u & 1);
+      tc_fence_after();
+      const uint32_t lraw = tmem_ld1(tOg + d);
+      tmem_ld_wait();
+      const float l = __uint_as_float(lraw);
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const int q = qt * FA_BQ + row;
+      const int b = bh / p.heads, h = bh % p.heads;
+      __half* orow = p.out + (long long)b * p.o_sb + (long long)q * p.o_sq + (long long)h * p.o_sh;
+      for (int c = half; c < (d + 15) / 16; c += 2) {
+        uint32_t o[16];
+        tmem_ld16(tOg + c * 16, o);
+        tmem_ld_wait();
+        if (q < p.Nq) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int col = c * 16 + h8 * 8;
+            if (col < d) {
+              uint4 v;
+              __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                hv[i] = __floats2half2_rn(__uint_as_float(o[h8 * 8 + 2 * i]) * inv,
+                                          __uint_as_float(o[h8 * 8 + 2 * i + 1]) * inv);
+              *reinterpret_cast<uint4*>(orow + col) = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();       // orders this item's TMEM reads before the arrive on p_ready of the next item
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_rt(tmem_base, 512u);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -434,6 +734,19 @@ static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t st) {
   return check_launch("pfd_flash_attn_f16");
 }
 
+template <int PM>
+static int launch_xattn_short(const XsParams& p, int grid, int smem, cudaStream_t st) {
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_short_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         xs_smem_bytes(64));
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(xattn_short): %s", cudaGetErrorString(e));
+    done = true;
+  }
+  launch_k(xattn_short_kernel<PM>, dim3(grid), dim3(XS_THREADS), (size_t)smem, st, p);
+  return check_launch("pfd_flash_attn_f16(short keys)");
+}
+
 }  // namespace pfd
 
 using namespace pfd;
@@ -448,6 +761,31 @@ extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, 
   for (int i = 0; i < 3; ++i)
     if (q_strides[i] % 8 || k_strides[i] % 8 || vt_strides[i] % 8)
       return set_error("pfd_flash_attn_f16: strides must be multiples of 8 elements");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Nk <= XS_NKP && d <= 48 && option("xattn_short", 1)) {
+    // cross-attention against a short context: persistent single-tile kernel (see xattn_short_kernel)
+    XsParams x;
+    memset(&x, 0, sizeof(x));
+    if (int rc = encode4d(&x.tmQ, q, d, Nq, heads, B, q_strides[2], q_strides[1], q_strides[0], FA_BQ, "Q")) return rc;
+    if (int rc = encode4d(&x.tmK, k, d, Nk, heads, B, k_strides[2], k_strides[1], k_strides[0], XS_NKP, "K")) return rc;
+    if (int rc = encode4d(&x.tmV, vt, Nk, d, heads, B, vt_strides[2], vt_strides[1], vt_strides[0], (cuuint32_t)d, "V^T")) return rc;
+    x.Nq = Nq; x.Nk = Nk; x.heads = heads; x.d = d;
+    x.nqt = (Nq + FA_BQ - 1) / FA_BQ;
+    const long long total = (long long)B * heads * x.nqt;
+    if (total > 0x7fffffffLL) return set_error("pfd_flash_attn_f16: problem too large");
+    x.total = (int)total;
+    x.scale = scale;
+    x.out = static_cast<__half*>(out);
+    x.o_sb = o_sb; x.o_sq = o_sq; x.o_sh = d;
+    const int sms = num_sms();
+    const int grid = x.total < sms ? x.total : sms;
+    const int smem = xs_smem_bytes((d + 16) & ~15);
+    const int pm = option("flash_poly_mod", FLASH_POLY_MOD_DEFAULT);
+    if (pm == 2) return launch_xattn_short<2>(x, grid, smem, st);
+    if (pm == 3) return launch_xattn_short<3>(x, grid, smem, st);
+    if (pm == 4) return launch_xattn_short<4>(x, grid, smem, st);
+    return launch_xattn_short<0>(x, grid, smem, st);
+  }
   FlashParams p;
   memset(&p, 0, sizeof(p));
   // strides = {batch, head, row} in elements; q/k rows run over d, vt rows (one per channel) run over the keys
@@ -460,7 +798,6 @@ extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, 
   p.out = static_cast<__half*>(out);
   p.o_sb = o_sb; p.o_sq = o_sq; p.o_sh = d;
   dim3 grid((Nq + FA_BQ - 1) / FA_BQ, (unsigned)((long long)B * heads));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d <= 64) {
     // d <= 64 is MUFU-bound: a share of the exponentials goes to the FMA pipe ("flash_poly_mod": every n-th pair)
     const int pm = option("flash_poly_mod", FLASH_POLY_MOD_DEFAULT);

@@ -30,12 +30,19 @@ constexpr int STAGE_A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int SMEM_BUDGET = 232448;         // 227 KiB opt-in limit per CTA
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_STG_BYTES = 1024;         // per epilogue warp: 16 rows x 64 B transpose buffer
-// alignment slack + barriers + epilogue transpose buffers + fp32 bias of the tile (double-buffered)
-constexpr int smem_fixed(int bn) { return 1024 + 256 + EPI_WARPS * EPI_STG_BYTES + 2 * bn * 4; }
+// TMA-store epilogue: every epilogue warp stages ITS share of the whole output tile (32 rows x up to ceil(BN/32)*16
+// columns, fp16) so that the residual can be TMA-loaded into the same slabs while the main loop runs
+constexpr int epi_stg_bytes(int bn, bool tmae) { return tmae ? 1024 * ((bn / 16 + 1) / 2) : EPI_STG_BYTES; }
+// alignment slack + barriers + epilogue staging buffers + fp32 bias of the tile (double-buffered)
+// (the TMA-store slabs must keep the 512-byte alignment of their swizzle pattern: the barrier block is padded to 1 KB)
+constexpr int bar_block_bytes(bool tmae) { return tmae ? 1024 : 256; }
+constexpr int smem_fixed(int bn, bool tmae) { return 1024 + bar_block_bytes(tmae) + EPI_WARPS * epi_stg_bytes(bn, tmae) + 2 * bn * 4; }
 
 struct alignas(64) GemmParams {
   CUtensorMap tmA[PFD_MAX_SEG];
   CUtensorMap tmB;
+  // TMA-store epilogue: output / residual rasters as 32-row slabs of 32 columns (SWIZZLE_64B) and 16 columns (SWIZZLE_32B)
+  CUtensorMap tmO32, tmO16, tmR32, tmR16;
   int nseg;
   int taps[PFD_MAX_SEG];
   int chunks[PFD_MAX_SEG];
@@ -62,13 +69,14 @@ struct alignas(64) GemmParams {
   int vec_ok;
 };
 
-template <int BN>
+template <int BN, bool TMAE = false>
 struct GemmCfg {
   static constexpr int STAGE_B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-  static constexpr int RAW_STAGES = (SMEM_BUDGET - smem_fixed(BN)) / STAGE_BYTES;
+  static constexpr int RAW_STAGES = (SMEM_BUDGET - smem_fixed(BN, TMAE)) / STAGE_BYTES;
   static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + smem_fixed(BN);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + smem_fixed(BN, TMAE);
+  static constexpr int WARP_STG = epi_stg_bytes(BN, TMAE);
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128u : (2 * BN <= 256 ? 256u : 512u);
   static_assert(STAGE_B_BYTES % 1024 == 0, "B stage must keep 1024-B swizzle alignment");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
@@ -160,10 +168,12 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 // LEAN = true: epilogue for 16-byte-vectorisable outputs (channel-last rows, optional head split) without split-K;
 // LEAN = false keeps the general path (element-strided outputs such as V^T, split-K partials).
-template <int BN, bool LEAN>
+// TMAE = true (implies LEAN, plain channel-last output, no GEGLU / split-K): the tile leaves through TMA stores and the
+// residual arrives through TMA loads (see the epilogue).
+template <int BN, bool LEAN, bool TMAE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, TMAE>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
 
@@ -180,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  auto res_bar = [&](int w) { return bars + 8u * (2 * STAGES + 5 + w); };    // one per epilogue warp (TMAE)
   volatile uint32_t* tmem_slot_g =
       reinterpret_cast<volatile uint32_t*>(gbase + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
 
@@ -189,6 +200,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
     tma_prefetch_desc(&p.tmB);
+    if (TMAE) {
+      tma_prefetch_desc(&p.tmO32);
+      tma_prefetch_desc(&p.tmO16);
+      if (p.residual) {
+        tma_prefetch_desc(&p.tmR32);
+        tma_prefetch_desc(&p.tmR16);
+      }
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -199,6 +218,8 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 256);
     }
+    if (TMAE)
+      for (int w = 0; w < EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -314,6 +335,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const int ch_begin = half_id == 0 ? 0 : (nch + 1) / 2;
     const int ch_end = half_id == 0 ? (nch + 1) / 2 : nch;
     const bool plain_cols = p.cdiv >= p.N;  // no head split: column offset = col * so_c0
+    uint32_t res_phase = 0;                 // TMAE: parity of this warp's residual barrier
     int it = 0;
     for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
       const int tile = work % total_tiles;
@@ -352,9 +374,9 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         //  * the residual is read in the same coalesced mapping, one run ahead (run 0: before the
         //    accumulator is ready), and added to the fp16-rounded result in fp16 - the reference's
         //    `x + conv(h)` on fp16 tensors.
-        const uint32_t fixed0 = base + STAGES * Cfg::STAGE_BYTES + 256;
-        const uint32_t stg = fixed0 + (warp - 2) * EPI_STG_BYTES;
-        const uint32_t sbias = fixed0 + EPI_WARPS * EPI_STG_BYTES + as * (BN * 4);
+        const uint32_t fixed0 = base + STAGES * Cfg::STAGE_BYTES + bar_block_bytes(TMAE);
+        const uint32_t stg = fixed0 + (warp - 2) * Cfg::WARP_STG;
+        const uint32_t sbias = fixed0 + EPI_WARPS * Cfg::WARP_STG + as * (BN * 4);
         const int et = threadIdx.x - 64;
         if (et < BN) {
           // GEGLU weights/bias are packed [value | gate] per n tile (pack_geglu): bias index n_tile * BN + j
@@ -442,6 +464,144 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             }
             __syncwarp();
           }
+          tc_fence_before();
+          mbar_arrive(tempty_bar(as));
+          continue;
+        }
+        if constexpr (TMAE) {
+          // ---------------- TMA-store epilogue.  This warp owns rows [32q, 32q+32) x columns [cbeg, cend) of the tile
+          // and a private staging area holding that share as slabs of 32 rows x 32 columns (2 KB, SWIZZLE_64B) plus at
+          // most one 16-column tail slab (1 KB, SWIZZLE_32B).  Per tile: (1) wait until the previous tile's stores have
+          // read the staging area, (2) one lane TMA-loads the residual slabs into it (arrives while the main loop of
+          // this tile is still running), (3) per slab: tcgen05.ld -> bias / row add / activation in fp32 -> fp16 ->
+          // fp16 add of the residual read back from the slab (the reference's `x + f(h)` on fp16 tensors) -> in-place
+          // st.shared (conflict-free in the swizzled layout) -> fence.proxy.async -> one lane issues the TMA store.
+          // Out-of-raster rows and columns >= N are clipped by the TMA unit, so there is no per-row predicate, no
+          // 64-bit address arithmetic and no global load/store instruction left in the loop.
+          const int r0 = q * 32;
+          const int gx = tx * p.bw + r0 % p.bw;
+          const int gy = ty * p.bh + (r0 / p.bw) % p.bh;
+          const int gn = tn * p.bn + r0 / (p.bw * p.bh);
+          int live32 = 0;
+          for (int i = 0; i < n32; ++i) live32 += (col_base + cbeg + 32 * i < n_lim) ? 1 : 0;
+          const bool live16 = tail16 && (col_base + cbeg + 32 * n32 < n_lim);
+          const uint32_t rb_addr = res_bar(warp - 2);
+          if (lane == 0) {
+            bulk_wait_read_all();                         // stores of the previous tile have read the slabs
+            if (has_res && (live32 > 0 || live16)) {
+              mbar_expect_tx(rb_addr, live32 * 2048 + (live16 ? 1024 : 0));
+              for (int i = 0; i < live32; ++i)
+                tma_load_4d(stg + i * 2048, &p.tmR32, rb_addr, col_base + cbeg + 32 * i, gx, gy, gn);
+              if (live16) tma_load_4d(stg + n32 * 2048, &p.tmR16, rb_addr, col_base + cbeg + 32 * n32, gx, gy, gn);
+            }
+          }
+          __syncwarp();
+          asm volatile("bar.sync 1, 256;" ::: "memory");          // bias of this tile visible to all epilogue warps
+          mbar_wait(tfull_bar(as), aph);
+          tc_fence_after();
+          if (has_res && (live32 > 0 || live16)) {
+            mbar_wait(rb_addr, res_phase);
+            res_phase ^= 1u;
+          }
+          const uint32_t sw64 = (lane >> 1) & 3, sw32 = (lane >> 2) & 1;
+          for (int i = 0; i < live32; ++i) {
+            const int c0 = cbeg + 32 * i;
+            uint32_t r[32];
+            tmem_ld32(taddr + c0, r);
+            tmem_ld_wait();
+            uint32_t h[16];
+            if (rowadd_row == nullptr && act == PFD_ACT_NONE) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 b = ld_shared_f4(sbias + (c0 + q4 * 4) * 4);
+                h[q4 * 2] = pack_h2(fmaf(__uint_as_float(r[q4 * 4]), alpha, b.x), fmaf(__uint_as_float(r[q4 * 4 + 1]), alpha, b.y));
+                h[q4 * 2 + 1] = pack_h2(fmaf(__uint_as_float(r[q4 * 4 + 2]), alpha, b.z), fmaf(__uint_as_float(r[q4 * 4 + 3]), alpha, b.w));
+              }
+            } else {
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                float v[8];
+                const float4 b0 = ld_shared_f4(sbias + (c0 + q8 * 8) * 4);
+                const float4 b1 = ld_shared_f4(sbias + (c0 + q8 * 8 + 4) * 4);
+                v[0] = fmaf(__uint_as_float(r[q8 * 8]), alpha, b0.x);
+                v[1] = fmaf(__uint_as_float(r[q8 * 8 + 1]), alpha, b0.y);
+                v[2] = fmaf(__uint_as_float(r[q8 * 8 + 2]), alpha, b0.z);
+                v[3] = fmaf(__uint_as_float(r[q8 * 8 + 3]), alpha, b0.w);
+                v[4] = fmaf(__uint_as_float(r[q8 * 8 + 4]), alpha, b1.x);
+                v[5] = fmaf(__uint_as_float(r[q8 * 8 + 5]), alpha, b1.y);
+                v[6] = fmaf(__uint_as_float(r[q8 * 8 + 6]), alpha, b1.z);
+                v[7] = fmaf(__uint_as_float(r[q8 * 8 + 7]), alpha, b1.w);
+                if (rowadd_row != nullptr && valid && col_base + c0 + q8 * 8 < n_lim) {
+                  float rv[8];
+                  load8h(rowadd_row + col_base + c0 + q8 * 8, rv);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) v[k] += rv[k];
+                }
+                if (act != PFD_ACT_NONE) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) v[k] = act_apply(v[k], act);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h[q8 * 4 + k] = pack_h2(v[2 * k], v[2 * k + 1]);
+              }
+            }
+            const uint32_t slab = stg + i * 2048 + lane * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t a = slab + ((k ^ sw64) << 4);
+              uint4 o = make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+              if (has_res) o = hadd2x4(o, ld_shared_v4(a));
+              st_shared_v4(a, o.x, o.y, o.z, o.w);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_4d(&p.tmO32, stg + i * 2048, col_base + c0, gx, gy, gn);
+          }
+          if (live16) {
+            const int c0 = cbeg + 32 * n32;
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            uint32_t h[8];
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+              float v[8];
+              const float4 b0 = ld_shared_f4(sbias + (c0 + q8 * 8) * 4);
+              const float4 b1 = ld_shared_f4(sbias + (c0 + q8 * 8 + 4) * 4);
+              v[0] = fmaf(__uint_as_float(r[q8 * 8]), alpha, b0.x);
+              v[1] = fmaf(__uint_as_float(r[q8 * 8 + 1]), alpha, b0.y);
+              v[2] = fmaf(__uint_as_float(r[q8 * 8 + 2]), alpha, b0.z);
+              v[3] = fmaf(__uint_as_float(r[q8 * 8 + 3]), alpha, b0.w);
+              v[4] = fmaf(__uint_as_float(r[q8 * 8 + 4]), alpha, b1.x);
+              v[5] = fmaf(__uint_as_float(r[q8 * 8 + 5]), alpha, b1.y);
+              v[6] = fmaf(__uint_as_float(r[q8 * 8 + 6]), alpha, b1.z);
+              v[7] = fmaf(__uint_as_float(r[q8 * 8 + 7]), alpha, b1.w);
+              if (rowadd_row != nullptr && valid && col_base + c0 + q8 * 8 < n_lim) {
+                float rv[8];
+                load8h(rowadd_row + col_base + c0 + q8 * 8, rv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += rv[k];
+              }
+              if (act != PFD_ACT_NONE) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = act_apply(v[k], act);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) h[q8 * 4 + k] = pack_h2(v[2 * k], v[2 * k + 1]);
+            }
+            const uint32_t slab = stg + n32 * 2048 + lane * 32;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t a = slab + ((k ^ sw32) << 4);
+              uint4 o = make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+              if (has_res) o = hadd2x4(o, ld_shared_v4(a));
+              st_shared_v4(a, o.x, o.y, o.z, o.w);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_4d(&p.tmO16, stg + n32 * 2048, col_base + c0, gx, gy, gn);
+          }
+          if (lane == 0) bulk_commit_group();
           tc_fence_before();
           mbar_arrive(tempty_bar(as));
           continue;
@@ -815,6 +975,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     }
   }
 
+  if (TMAE && warp >= 2 && lane == 0) bulk_wait_all();       // this thread's TMA stores have been performed
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -948,12 +1109,13 @@ static EncodeTiledFn get_encode_fn() {
 
 static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box,
-                      const cuuint32_t* estr, const char* what) {
+                      const cuuint32_t* estr, const char* what,
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims,
                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return set_error(
@@ -970,18 +1132,39 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
 
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
-template <int BN, bool LEAN>
+template <int BN, bool LEAN, bool TMAE>
 static int launch_gemm_t(const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, TMAE>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN, TMAE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_done = true;
   }
-  launch_k(gemm_tc_kernel<BN, LEAN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
+  launch_k(gemm_tc_kernel<BN, LEAN, TMAE>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
   return check_launch("pfd_gemm_f16");
+}
+
+// Output (and residual) rasters as TMA tensor maps for the TMA-store epilogue: dims {N, W, H, NB}, one box = the 32
+// consecutive tile rows of an epilogue warp (sbw x sbh x sbn pixels) x 32 or 16 channels.
+static int encode_epilogue_maps(GemmParams& p, const pfd_gemm_desc* d) {
+  const int sbw = p.bw < 32 ? p.bw : 32;
+  const int sbh = p.bh < 32 / sbw ? p.bh : 32 / sbw;
+  const int sbn = 32 / (sbw * sbh);
+  const long long sx = d->so_x, sy = d->H > 1 ? d->so_y : sx * d->W, sn = d->NB > 1 ? d->so_n1 : sy * d->H;
+  cuuint64_t dims[4] = {(cuuint64_t)d->N, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->NB};
+  cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sn * 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint32_t box32[4] = {32, (cuuint32_t)sbw, (cuuint32_t)sbh, (cuuint32_t)sbn};
+  cuuint32_t box16[4] = {16, (cuuint32_t)sbw, (cuuint32_t)sbh, (cuuint32_t)sbn};
+  if (int rc = encode_map(&p.tmO32, d->out, 4, dims, strides, box32, estr, "out32", CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  if (int rc = encode_map(&p.tmO16, d->out, 4, dims, strides, box16, estr, "out16", CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+  if (d->residual) {
+    if (int rc = encode_map(&p.tmR32, d->residual, 4, dims, strides, box32, estr, "res32", CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    if (int rc = encode_map(&p.tmR16, d->residual, 4, dims, strides, box16, estr, "res16", CU_TENSOR_MAP_SWIZZLE_32B)) return rc;
+  }
+  return 0;
 }
 
 static inline bool gemm_lean_enabled() {
@@ -994,8 +1177,18 @@ static inline bool gemm_lean_enabled() {
 }
 
 template <int BN>
-static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream, const pfd_gemm_desc* d) {
   const bool lean = gemm_lean_enabled() && p.vec_ok && p.splits == 1;
+  // TMA-store epilogue: plain channel-last output raster (no head / batch split), not GEGLU, tile staging fits (BN <= 192)
+  bool tmae = false;
+  if constexpr (BN <= 192) {
+    tmae = lean && p.cdiv >= p.N && p.ndiv == 1 && p.act != PFD_ACT_GEGLU && option("gemm_tma_epi", 1) &&
+           (d->H == 1 || d->so_y >= (long long)d->so_x * d->W) && (d->NB == 1 || d->so_n1 > 0);
+    if (tmae && encode_epilogue_maps(p, d)) {
+      tmae = false;                       // raster not expressible as a tensor map: keep the register epilogue
+      g_last_error.clear();
+    }
+  }
   static int trace = -1;
   if (trace < 0) {
     const char* e = getenv("PFD_GEMM_TRACE");
@@ -1003,10 +1196,13 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
   }
   if (trace)   // one line per launch, joined with an ncu launch list by tools/gemm_breakdown.py
     fprintf(stderr, "GEMMTRACE M=%lld N=%d K=%d nseg=%d taps=%d stride=%d act=%d bias=%d res=%d rowadd=%d BN=%d lean=%d "
-            "splits=%d grid=%d batched=%d vec=%d plain=%d\n", (long long)p.W * p.H * p.NB, p.N, p.num_kb * BK, p.nseg,
+            "splits=%d grid=%d batched=%d vec=%d plain=%d tmae=%d\n", (long long)p.W * p.H * p.NB, p.N, p.num_kb * BK, p.nseg,
             p.taps[0], p.stride, p.act, p.bias != nullptr, p.residual != nullptr, p.rowadd != nullptr, BN, (int)lean,
-            p.splits, grid, p.b_batched, p.vec_ok, (int)(p.cdiv >= p.N));
-  return lean ? launch_gemm_t<BN, true>(p, grid, stream) : launch_gemm_t<BN, false>(p, grid, stream);
+            p.splits, grid, p.b_batched, p.vec_ok, (int)(p.cdiv >= p.N), (int)tmae);
+  if constexpr (BN <= 192) {
+    if (tmae) return launch_gemm_t<BN, true, true>(p, grid, stream);
+  }
+  return lean ? launch_gemm_t<BN, true, false>(p, grid, stream) : launch_gemm_t<BN, false, false>(p, grid, stream);
 }
 
 }  // namespace pfd
@@ -1164,11 +1360,11 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   int grid = (int)(total < sms ? total : sms);
   int rc;
   switch (BNsel) {
-    case 64: rc = launch_gemm<64>(p, grid, st); break;
-    case 128: rc = launch_gemm<128>(p, grid, st); break;
-    case 160: rc = launch_gemm<160>(p, grid, st); break;
-    case 192: rc = launch_gemm<192>(p, grid, st); break;
-    default: rc = launch_gemm<256>(p, grid, st); break;
+    case 64: rc = launch_gemm<64>(p, grid, st, d); break;
+    case 128: rc = launch_gemm<128>(p, grid, st, d); break;
+    case 160: rc = launch_gemm<160>(p, grid, st, d); break;
+    case 192: rc = launch_gemm<192>(p, grid, st, d); break;
+    default: rc = launch_gemm<256>(p, grid, st, d); break;
   }
   if (rc || p.splits == 1) return rc;
   const long long vec_items = m_tiles * BM * (long long)(d->N / 8);

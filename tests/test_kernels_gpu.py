@@ -66,6 +66,68 @@ def test_linear_two_segments(nv):
     close(out, torch.cat([x1, x2], 1).float() @ w.float().t())
 
 
+@pytest.mark.parametrize("case", ["linear_res", "linear_narrow", "linear_ragged", "linear_slice", "conv_res", "conv_small",
+                                  "conv_rowadd_silu", "conv_stride2", "bmm"])
+def test_gemm_tma_store_epilogue_bit_exact(nv, case):
+    """The TMA-store epilogue (tile staged in swizzled shared-memory slabs, residual TMA-loaded into the same slabs,
+    cp.async.bulk.tensor stores, clipping by the TMA unit) must produce EXACTLY the bits of the register epilogue
+    (option gemm_tma_epi = 0) - same fp32 math, same fp16 rounding points - for every raster tiling: 128x1x1 rows
+    (Linear), 8x8x2 / 16x8 / 32x4 pixel tiles (convs), ragged rows / columns, N not a multiple of the tile, an output
+    that is a column slice of a wider tensor, per-image row add + activation, and batched B."""
+    def run():
+        if case == "linear_res":
+            x, w, b, r = rnd(4096, 320), rnd(320, 320, scale=320 ** -0.5, seed=1), rnd(320, seed=2), rnd(4096, 320, seed=3)
+            return nv.linear(x, w, b, residual=r), x.float() @ w.float().t() + b.float() + r.float()
+        if case == "linear_narrow":
+            x, w, b = rnd(512, 40), rnd(24, 40, scale=40 ** -0.5, seed=1), rnd(24, seed=2)
+            return nv.linear(x, w, b), x.float() @ w.float().t() + b.float()
+        if case == "linear_ragged":
+            x, w, r = rnd(1000, 768), rnd(1288, 768, scale=768 ** -0.5, seed=1), rnd(1000, 1288, seed=3)
+            return nv.linear(x, w, None, residual=r), x.float() @ w.float().t() + r.float()
+        if case == "linear_slice":
+            x, w, b = rnd(300, 192), rnd(320, 192, scale=192 ** -0.5, seed=1), rnd(320, seed=2)
+            big = torch.full((300, 1024), 7.0, device="cuda", dtype=torch.float16)
+            out = nv.linear(x, w, b, out=big[:, 128:448])
+            assert (big[:, :128] == 7).all() and (big[:, 448:] == 7).all()
+            return out.contiguous(), x.float() @ w.float().t() + b.float()
+        if case in ("conv_res", "conv_small", "conv_rowadd_silu", "conv_stride2"):
+            NB, H, W, C, N = {"conv_res": (2, 64, 64, 320, 320), "conv_small": (3, 8, 8, 128, 192),
+                              "conv_rowadd_silu": (2, 24, 24, 64, 160), "conv_stride2": (2, 32, 32, 64, 128)}[case]
+            x = rnd(NB, H, W, C)
+            w4 = rnd(N, C, 3, 3, scale=(9 * C) ** -0.5, seed=1)
+            b = rnd(N, seed=2)
+            wp = w4.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+            xr = x.float().permute(0, 3, 1, 2)
+            if case == "conv_stride2":
+                out = nv.conv3x3(x, wp, b, stride=2)
+                ref = F.conv2d(xr, w4.float(), b.float(), stride=2, padding=1)
+            elif case == "conv_rowadd_silu":
+                ra = rnd(NB, N, seed=5)
+                out = nv.conv3x3(x, wp, b, rowadd=ra, act=nv.ACT_SILU)
+                ref = F.silu(F.conv2d(xr, w4.float(), b.float(), padding=1) + ra.float()[:, :, None, None])
+            else:
+                r = rnd(NB, H, W, N, seed=3)
+                out = nv.conv3x3(x, wp, b, residual=r)
+                ref = F.conv2d(xr, w4.float(), b.float(), padding=1) + r.float().permute(0, 3, 1, 2)
+            return out, ref.permute(0, 2, 3, 1)
+        q, k = rnd(6, 200, 64), rnd(6, 136, 64, seed=1)
+        s_ = torch.empty((6, 200, 136), device="cuda", dtype=torch.float16)
+        nv.gemm_raw([(q, 1, 64, (64, 64 * 200, 64 * 200))], in_w=200, in_h=1, stride=1, W=200, H=1, NB=6, w=k, N=136, K=64,
+                    b_batch_stride=136 * 64, out=s_, so=(200 * 136, 0, 0, 136, 0, 1))
+        return s_, torch.bmm(q.float(), k.float().transpose(1, 2))
+    nv.set_env_option(None, None)
+    try:
+        nv.set_env_option("gemm_tma_epi", 0)
+        out0, ref = run()
+        out0 = out0.clone()
+    finally:
+        nv.set_env_option(None, None)
+    out1, _ = run()
+    torch.cuda.synchronize()
+    close(out0, ref)
+    assert torch.equal(out0, out1), f"TMA-store epilogue differs from the register epilogue: max |d| = {(out0.float() - out1.float()).abs().max().item()}"
+
+
 @pytest.mark.parametrize("C", [64, 320])
 def test_geglu(nv, C):
     M, inner = 512, 4 * C
@@ -293,6 +355,46 @@ def test_flash_attention(nv, B, heads, Nq, Nk, d):
     close(o_unfused, ref, rtol=6e-3, atol=2e-3)
     # flash path: packed-half2 exp (MUFU.EX2.F16) -> probabilities carry ~2^-11 relative error
     close(o_flash, ref, rtol=8e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", [(8, 8, 4096, 148, 40), (2, 8, 1000, 148, 40), (3, 4, 64, 148, 40),
+                                             (1, 2, 300, 77, 40), (2, 3, 130, 160, 48), (1, 5, 257, 20, 8),
+                                             (1, 1, 128, 33, 16), (2, 8, 9216, 148, 40)])
+def test_short_key_attention(nv, B, heads, Nq, Nk, d):
+    """Cross-attention against a short context (Nk <= 160, d <= 48): the persistent single-score-tile kernel
+    (xattn_short_kernel: contiguous (batch*head, query tile) ranges per CTA, K / V^T resident per head, two softmax
+    groups) against an fp32 torch reference and against the generic flash kernel on the same operands.  Shapes cover
+    the BASELINE level-0 launches (512x512: 4096 queries, 768x768: 9216), ragged query counts, one query tile per
+    head (a K / V^T reload for every item), partial / full last key chunk and the smallest head dims."""
+    g = torch.Generator().manual_seed(Nq + Nk)
+    q = torch.randn((B * heads, Nq, d), generator=g).cuda().half()
+    Nkp = (Nk + 7) // 8 * 8
+    k = torch.zeros((B * heads, Nkp, d), device="cuda", dtype=torch.float16)
+    k[:, :Nk] = torch.randn((B * heads, Nk, d), generator=g).cuda().half()
+    vt = torch.zeros((B * heads, d, Nkp), device="cuda", dtype=torch.float16)
+    vt[:, :, :Nk] = torch.randn((B * heads, d, Nk), generator=g).cuda().half()
+    scale = d ** -0.5
+    out_s = torch.full((B, Nq, heads * d), float("nan"), device="cuda", dtype=torch.float16)
+    out_f = torch.empty_like(out_s)
+    nv.set_env_option(None, None)
+    n0 = nv.launch_count()
+    nv.flash_attn(q, k, vt, B=B, heads=heads, Nq=Nq, Nk=Nk, scale=scale, out=out_s)
+    assert nv.launch_count() == n0 + 1
+    try:
+        nv.set_env_option("xattn_short", 0)
+        nv.flash_attn(q, k, vt, B=B, heads=heads, Nq=Nq, Nk=Nk, scale=scale, out=out_f)
+    finally:
+        nv.set_env_option(None, None)
+    torch.cuda.synchronize()
+    s = (torch.bmm(q.float(), k[:, :Nk].float().transpose(1, 2)).half().float() * scale).half().float()
+    ref = torch.bmm(torch.softmax(s, -1), vt[:, :, :Nk].float().transpose(1, 2))
+    ref = ref.reshape(B, heads, Nq, d).permute(0, 2, 1, 3).reshape(B, Nq, heads * d)
+    assert torch.isfinite(out_s.float()).all()
+    close(out_s, ref, rtol=8e-3, atol=4e-3)
+    es = ((out_s.float() - ref).pow(2).mean() / ref.pow(2).mean()).sqrt().item()
+    ef = ((out_f.float() - ref).pow(2).mean() / ref.pow(2).mean()).sqrt().item()
+    print(f"[short-key attention] B={B} h={heads} {Nq}x{Nk} d={d}: rel rms short {es:.2e}  generic flash {ef:.2e}")
+    assert es < max(1.5 * ef, 1.5e-3)
 
 
 @pytest.mark.parametrize("B,heads,N,d", [(2, 8, 4096, 40), (2, 8, 1024, 80), (1, 8, 256, 160), (3, 4, 64, 40)])

@@ -26,7 +26,10 @@ def main(csv_path, trace_path):
                 tr.append(seg)
             seg = []
         elif l.startswith("GEMMTRACE"):
-            seg.append(dict(kv.split("=") for kv in l.split()[1:]))
+            dd = dict(kv.split("=") for kv in l.split()[1:])
+            if dd.get("tmae") == "1":
+                dd["lean"] = "T"                      # lean epilogue with TMA stores / TMA-loaded residual
+            seg.append(dd)
     last = tr[-1]
     times = gemm[-len(last):]          # the last evaluation's launches are the last GEMM rows of the list
     agg = OrderedDict()
