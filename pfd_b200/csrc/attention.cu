@@ -409,7 +409,6 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
 // after it has read S_g completely and (one item earlier) drained O_g, and the issuer orders S(i+2) and PV(i+2)
 // behind the wait on p_ready(i) / p_ready(i+2).
 constexpr int XS_NKP = 160;        // score tile width (keys, padded to the UMMA N granule of 16)
-constexpr int XS_WAIT_HINT_DEFAULT = 4096;
 constexpr int XS_THREADS = 64 + 2 * 256;   // TMA warp, MMA warp, 2 softmax groups of 8 warps
 constexpr int XS_Q_BYTES = FA_BQ * 128;
 constexpr int XS_K_BYTES = XS_NKP * 128;
@@ -426,8 +425,7 @@ struct alignas(64) XsParams {
 
 static int xs_smem_bytes(int dN) { return 2 * XS_Q_BYTES + 2 * XS_K_BYTES + 2 * 3 * dN * 128 + 2 * XS_P_BYTES + 1024 + 256 + 2048; }
 
-// WH = suspend-time hint (ns) of this kernel's mbarrier waits (0 = none): every hand-off here is on the critical path
-template <int PM, uint32_t WH>
+template <int PM>
 __global__ void __launch_bounds__(XS_THREADS, 1)
 xattn_short_kernel(const __grid_constant__ XsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -513,7 +511,7 @@ xattn_short_kernel(const __grid_constant__ XsParams p) {
           ++kvn;
           prev_bh = bh;
           const int ks = kvn & 1, ku = kvn >> 1;
-          if (ku >= 1) mbar_wait_h<WH>(kv_empty(ks), (ku - 1) & 1);     // every MMA that read the slot has completed
+          if (ku >= 1) mbar_wait(kv_empty(ks), (ku - 1) & 1);     // every MMA that read the slot has completed
           const int nvc = (p.Nk + 63) >> 6;                       // 64-key chunks of V^T that hold valid keys
           mbar_expect_tx(kv_full(ks), XS_K_BYTES + nvc * d * 128);
           tma_load_4d(sK + ks * XS_K_BYTES, &p.tmK, kv_full(ks), 0, 0, hb, bb);
@@ -521,7 +519,7 @@ xattn_short_kernel(const __grid_constant__ XsParams p) {
             tma_load_4d(sV + ks * V_BYTES + c * VC_BYTES, &p.tmV, kv_full(ks), c * 64, 0, hb, bb);
         }
         const int qs = li & 1, qu = li >> 1;
-        if (qu >= 1) mbar_wait_h<WH>(q_empty(qs), (qu - 1) & 1);        // S of item li - 2 has read the slot
+        if (qu >= 1) mbar_wait(q_empty(qs), (qu - 1) & 1);        // S of item li - 2 has read the slot
         mbar_expect_tx(q_full(qs), XS_Q_BYTES);
         tma_load_4d(sQ + qs * XS_Q_BYTES, &p.tmQ, q_full(qs), 0, qt * FA_BQ, hb, bb);
       }
@@ -540,8 +538,8 @@ xattn_short_kernel(const __grid_constant__ XsParams p) {
           s_prev = bh;
         }
         const int g = li & 1, u = li >> 1;
-        mbar_wait_h<WH>(q_full(g), u & 1);
-        mbar_wait_h<WH>(kv_full(s_kvn & 1), (s_kvn >> 1) & 1);
+        mbar_wait(q_full(g), u & 1);
+        mbar_wait(kv_full(s_kvn & 1), (s_kvn >> 1) & 1);
         tc_fence_after();
         const uint64_t ad = make_sw128_kmajor_desc(sQ + g * XS_Q_BYTES);
         const uint64_t bd = make_sw128_kmajor_desc(sK + (s_kvn & 1) * XS_K_BYTES);
@@ -556,7 +554,7 @@ xattn_short_kernel(const __grid_constant__ XsParams p) {
           o_prev = bh;
         }
         const int g = li & 1, u = li >> 1;
-        mbar_wait_h<WH>(p_ready(g), u & 1);
+        mbar_wait(p_ready(g), u & 1);
         tc_fence_after();
         for (int s = 0; s < ksteps_o; ++s) {
           const int c = s >> 2, k4 = s & 3;
@@ -598,7 +596,7 @@ xattn_short_kernel(const __grid_constant__ XsParams p) {
       const int u = li >> 1;
       const int item = lo + li;
       const int bh = item / p.nqt, qt = item % p.nqt;
-      mbar_wait_h<WH>(s_full(g), u & 1);
+      mbar_wait(s_full(g), u & 1);
       tc_fence_after();
       uint32_t r[80];
       tmem_ld32(tSg, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
@@ -651,7 +649,7 @@ xattn_short_kernel(const __grid_constant__ XsParams p) {
       mbar_arrive(p_ready(g));
       // ---- epilogue of this item: O / l -> [B, Nq, heads*d]   (l = column d of the accumulator); the two threads
       //      of a row take alternate 16-column chunks of O
-      mbar_wait_h<WH>(o_full(g), u & 1);
+      mbar_wait(o_full(g), u & 1);
       tc_fence_after();
       const uint32_t lraw = tmem_ld1(tOg + d);
       tmem_ld_wait();
@@ -736,16 +734,16 @@ static int launch_flash(const FlashParams& p, dim3 grid, cudaStream_t st) {
   return check_launch("pfd_flash_attn_f16");
 }
 
-template <int PM, uint32_t WH>
+template <int PM>
 static int launch_xattn_short(const XsParams& p, int grid, int smem, cudaStream_t st) {
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_short_kernel<PM, WH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(xattn_short_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          xs_smem_bytes(64));
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(xattn_short): %s", cudaGetErrorString(e));
     done = true;
   }
-  launch_k(xattn_short_kernel<PM, WH>, dim3(grid), dim3(XS_THREADS), (size_t)smem, st, p);
+  launch_k(xattn_short_kernel<PM>, dim3(grid), dim3(XS_THREADS), (size_t)smem, st, p);
   return check_launch("pfd_flash_attn_f16(short keys)");
 }
 
@@ -783,12 +781,8 @@ extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, 
     const int grid = x.total < sms ? x.total : sms;
     const int smem = xs_smem_bytes((d + 16) & ~15);
     const int pm = option("flash_poly_mod", FLASH_POLY_MOD_DEFAULT);
-    const int wh = option("xattn_wait_hint", XS_WAIT_HINT_DEFAULT);
-    if (pm == 4) return launch_xattn_short<4, XS_WAIT_HINT_DEFAULT>(x, grid, smem, st);
-    if (wh == 0) return launch_xattn_short<0, 0>(x, grid, smem, st);
-    if (wh == 32) return launch_xattn_short<0, 32>(x, grid, smem, st);
-    if (wh == 256) return launch_xattn_short<0, 256>(x, grid, smem, st);
-    return launch_xattn_short<0, 4096>(x, grid, smem, st);
+    if (pm == 4) return launch_xattn_short<4>(x, grid, smem, st);
+    return launch_xattn_short<0>(x, grid, smem, st);
   }
   FlashParams p;
   memset(&p, 0, sizeof(p));

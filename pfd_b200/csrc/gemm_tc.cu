@@ -166,6 +166,163 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Per-warp view of one output tile for the TMA-store epilogue (shared by the single-CTA and the CTA-pair kernel).
+struct EpiTile {
+  int q, lane;                 // TMEM lane quarter / lane of the warp
+  int tx, ty, tn;              // raster tile coordinates
+  int cbeg, n32;               // first column of this warp inside the tile, number of 32-column runs
+  bool tail16;                 // a 16-column tail run follows
+  int col_base, n_lim;         // first output column of the tile, number of valid output columns
+  bool has_res, valid;
+  uint32_t stg, rbar, tfull, aph, taddr, sbias;
+  float alpha;
+  int act;
+  const __half* rowadd_row;
+};
+
+// ---------------- TMA-store epilogue.  This warp owns rows [32q, 32q+32) x columns [cbeg, cend) of the tile
+// and a private staging area holding that share as slabs of 32 rows x 32 columns (2 KB, SWIZZLE_64B) plus at
+// most one 16-column tail slab (1 KB, SWIZZLE_32B).  Per tile: (1) wait until the previous tile's stores have
+// read the staging area, (2) one lane TMA-loads the residual slabs into it (arrives while the main loop of
+// this tile is still running), (3) per slab: tcgen05.ld -> bias / row add / activation in fp32 -> fp16 ->
+// fp16 add of the residual read back from the slab (the reference's `x + f(h)` on fp16 tensors) -> in-place
+// st.shared (conflict-free in the swizzled layout) -> fence.proxy.async -> one lane issues the TMA store.
+// Out-of-raster rows and columns >= N are clipped by the TMA unit, so there is no per-row predicate, no
+// 64-bit address arithmetic and no global load/store instruction left in the loop.
+template <int BN>
+__device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const EpiTile& e, uint32_t& res_phase) {
+  const int q = e.q, lane = e.lane, tx = e.tx, ty = e.ty, tn = e.tn, cbeg = e.cbeg, n32 = e.n32;
+  const bool tail16 = e.tail16, has_res = e.has_res, valid = e.valid;
+  const int col_base = e.col_base, n_lim = e.n_lim, act = e.act;
+  const uint32_t stg = e.stg, taddr = e.taddr, sbias = e.sbias;
+  const float alpha = e.alpha;
+  const __half* rowadd_row = e.rowadd_row;
+  const int r0 = q * 32;
+  const int gx = tx * p.bw + r0 % p.bw;
+  const int gy = ty * p.bh + (r0 / p.bw) % p.bh;
+  const int gn = tn * p.bn + r0 / (p.bw * p.bh);
+  int live32 = 0;
+  for (int i = 0; i < n32; ++i) live32 += (col_base + cbeg + 32 * i < n_lim) ? 1 : 0;
+  const bool live16 = tail16 && (col_base + cbeg + 32 * n32 < n_lim);
+  const uint32_t rb_addr = e.rbar;
+  if (lane == 0) {
+    bulk_wait_read_all();                         // stores of the previous tile have read the slabs
+    if (has_res && (live32 > 0 || live16)) {
+      mbar_expect_tx(rb_addr, live32 * 2048 + (live16 ? 1024 : 0));
+      for (int i = 0; i < live32; ++i)
+        tma_load_4d(stg + i * 2048, &p.tmR32, rb_addr, col_base + cbeg + 32 * i, gx, gy, gn);
+      if (live16) tma_load_4d(stg + n32 * 2048, &p.tmR16, rb_addr, col_base + cbeg + 32 * n32, gx, gy, gn);
+    }
+  }
+  __syncwarp();
+  asm volatile("bar.sync 1, 256;" ::: "memory");          // bias of this tile visible to all epilogue warps
+  mbar_wait(e.tfull, e.aph);
+  tc_fence_after();
+  if (has_res && (live32 > 0 || live16)) {
+    mbar_wait(rb_addr, res_phase);
+    res_phase ^= 1u;
+  }
+  const uint32_t sw64 = (lane >> 1) & 3, sw32 = (lane >> 2) & 1;
+  for (int i = 0; i < live32; ++i) {
+    const int c0 = cbeg + 32 * i;
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);
+    tmem_ld_wait();
+    uint32_t h[16];
+    if (rowadd_row == nullptr && act == PFD_ACT_NONE) {
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 b = ld_shared_f4(sbias + (c0 + q4 * 4) * 4);
+        h[q4 * 2] = pack_h2(fmaf(__uint_as_float(r[q4 * 4]), alpha, b.x), fmaf(__uint_as_float(r[q4 * 4 + 1]), alpha, b.y));
+        h[q4 * 2 + 1] = pack_h2(fmaf(__uint_as_float(r[q4 * 4 + 2]), alpha, b.z), fmaf(__uint_as_float(r[q4 * 4 + 3]), alpha, b.w));
+      }
+    } else {
+#pragma unroll
+      for (int q8 = 0; q8 < 4; ++q8) {
+        float v[8];
+        const float4 b0 = ld_shared_f4(sbias + (c0 + q8 * 8) * 4);
+        const float4 b1 = ld_shared_f4(sbias + (c0 + q8 * 8 + 4) * 4);
+        v[0] = fmaf(__uint_as_float(r[q8 * 8]), alpha, b0.x);
+        v[1] = fmaf(__uint_as_float(r[q8 * 8 + 1]), alpha, b0.y);
+        v[2] = fmaf(__uint_as_float(r[q8 * 8 + 2]), alpha, b0.z);
+        v[3] = fmaf(__uint_as_float(r[q8 * 8 + 3]), alpha, b0.w);
+        v[4] = fmaf(__uint_as_float(r[q8 * 8 + 4]), alpha, b1.x);
+        v[5] = fmaf(__uint_as_float(r[q8 * 8 + 5]), alpha, b1.y);
+        v[6] = fmaf(__uint_as_float(r[q8 * 8 + 6]), alpha, b1.z);
+        v[7] = fmaf(__uint_as_float(r[q8 * 8 + 7]), alpha, b1.w);
+        if (rowadd_row != nullptr && valid && col_base + c0 + q8 * 8 < n_lim) {
+          float rv[8];
+          load8h(rowadd_row + col_base + c0 + q8 * 8, rv);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] += rv[k];
+        }
+        if (act != PFD_ACT_NONE) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = act_apply(v[k], act);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[q8 * 4 + k] = pack_h2(v[2 * k], v[2 * k + 1]);
+      }
+    }
+    const uint32_t slab = stg + i * 2048 + lane * 64;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t a = slab + ((k ^ sw64) << 4);
+      uint4 o = make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+      if (has_res) o = hadd2x4(o, ld_shared_v4(a));
+      st_shared_v4(a, o.x, o.y, o.z, o.w);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) tma_store_4d(&p.tmO32, stg + i * 2048, col_base + c0, gx, gy, gn);
+  }
+  if (live16) {
+    const int c0 = cbeg + 32 * n32;
+    uint32_t r[16];
+    tmem_ld16(taddr + c0, r);
+    tmem_ld_wait();
+    uint32_t h[8];
+#pragma unroll
+    for (int q8 = 0; q8 < 2; ++q8) {
+      float v[8];
+      const float4 b0 = ld_shared_f4(sbias + (c0 + q8 * 8) * 4);
+      const float4 b1 = ld_shared_f4(sbias + (c0 + q8 * 8 + 4) * 4);
+      v[0] = fmaf(__uint_as_float(r[q8 * 8]), alpha, b0.x);
+      v[1] = fmaf(__uint_as_float(r[q8 * 8 + 1]), alpha, b0.y);
+      v[2] = fmaf(__uint_as_float(r[q8 * 8 + 2]), alpha, b0.z);
+      v[3] = fmaf(__uint_as_float(r[q8 * 8 + 3]), alpha, b0.w);
+      v[4] = fmaf(__uint_as_float(r[q8 * 8 + 4]), alpha, b1.x);
+      v[5] = fmaf(__uint_as_float(r[q8 * 8 + 5]), alpha, b1.y);
+      v[6] = fmaf(__uint_as_float(r[q8 * 8 + 6]), alpha, b1.z);
+      v[7] = fmaf(__uint_as_float(r[q8 * 8 + 7]), alpha, b1.w);
+      if (rowadd_row != nullptr && valid && col_base + c0 + q8 * 8 < n_lim) {
+        float rv[8];
+        load8h(rowadd_row + col_base + c0 + q8 * 8, rv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += rv[k];
+      }
+      if (act != PFD_ACT_NONE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = act_apply(v[k], act);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) h[q8 * 4 + k] = pack_h2(v[2 * k], v[2 * k + 1]);
+    }
+    const uint32_t slab = stg + n32 * 2048 + lane * 32;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t a = slab + ((k ^ sw32) << 4);
+      uint4 o = make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+      if (has_res) o = hadd2x4(o, ld_shared_v4(a));
+      st_shared_v4(a, o.x, o.y, o.z, o.w);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) tma_store_4d(&p.tmO16, stg + n32 * 2048, col_base + c0, gx, gy, gn);
+  }
+  if (lane == 0) bulk_commit_group();
+}
+
 // LEAN = true: epilogue for 16-byte-vectorisable outputs (channel-last rows, optional head split) without split-K;
 // LEAN = false keeps the general path (element-strided outputs such as V^T, split-K partials).
 // TMAE = true (implies LEAN, plain channel-last output, no GEGLU / split-K): the tile leaves through TMA stores and the
@@ -469,139 +626,12 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           continue;
         }
         if constexpr (TMAE) {
-          // ---------------- TMA-store epilogue.  This warp owns rows [32q, 32q+32) x columns [cbeg, cend) of the tile
-          // and a private staging area holding that share as slabs of 32 rows x 32 columns (2 KB, SWIZZLE_64B) plus at
-          // most one 16-column tail slab (1 KB, SWIZZLE_32B).  Per tile: (1) wait until the previous tile's stores have
-          // read the staging area, (2) one lane TMA-loads the residual slabs into it (arrives while the main loop of
-          // this tile is still running), (3) per slab: tcgen05.ld -> bias / row add / activation in fp32 -> fp16 ->
-          // fp16 add of the residual read back from the slab (the reference's `x + f(h)` on fp16 tensors) -> in-place
-          // st.shared (conflict-free in the swizzled layout) -> fence.proxy.async -> one lane issues the TMA store.
-          // Out-of-raster rows and columns >= N are clipped by the TMA unit, so there is no per-row predicate, no
-          // 64-bit address arithmetic and no global load/store instruction left in the loop.
-          const int r0 = q * 32;
-          const int gx = tx * p.bw + r0 % p.bw;
-          const int gy = ty * p.bh + (r0 / p.bw) % p.bh;
-          const int gn = tn * p.bn + r0 / (p.bw * p.bh);
-          int live32 = 0;
-          for (int i = 0; i < n32; ++i) live32 += (col_base + cbeg + 32 * i < n_lim) ? 1 : 0;
-          const bool live16 = tail16 && (col_base + cbeg + 32 * n32 < n_lim);
-          const uint32_t rb_addr = res_bar(warp - 2);
-          if (lane == 0) {
-            bulk_wait_read_all();                         // stores of the previous tile have read the slabs
-            if (has_res && (live32 > 0 || live16)) {
-              mbar_expect_tx(rb_addr, live32 * 2048 + (live16 ? 1024 : 0));
-              for (int i = 0; i < live32; ++i)
-                tma_load_4d(stg + i * 2048, &p.tmR32, rb_addr, col_base + cbeg + 32 * i, gx, gy, gn);
-              if (live16) tma_load_4d(stg + n32 * 2048, &p.tmR16, rb_addr, col_base + cbeg + 32 * n32, gx, gy, gn);
-            }
-          }
-          __syncwarp();
-          asm volatile("bar.sync 1, 256;" ::: "memory");          // bias of this tile visible to all epilogue warps
-          mbar_wait(tfull_bar(as), aph);
-          tc_fence_after();
-          if (has_res && (live32 > 0 || live16)) {
-            mbar_wait(rb_addr, res_phase);
-            res_phase ^= 1u;
-          }
-          const uint32_t sw64 = (lane >> 1) & 3, sw32 = (lane >> 2) & 1;
-          for (int i = 0; i < live32; ++i) {
-            const int c0 = cbeg + 32 * i;
-            uint32_t r[32];
-            tmem_ld32(taddr + c0, r);
-            tmem_ld_wait();
-            uint32_t h[16];
-            if (rowadd_row == nullptr && act == PFD_ACT_NONE) {
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 b = ld_shared_f4(sbias + (c0 + q4 * 4) * 4);
-                h[q4 * 2] = pack_h2(fmaf(__uint_as_float(r[q4 * 4]), alpha, b.x), fmaf(__uint_as_float(r[q4 * 4 + 1]), alpha, b.y));
-                h[q4 * 2 + 1] = pack_h2(fmaf(__uint_as_float(r[q4 * 4 + 2]), alpha, b.z), fmaf(__uint_as_float(r[q4 * 4 + 3]), alpha, b.w));
-              }
-            } else {
-#pragma unroll
-              for (int q8 = 0; q8 < 4; ++q8) {
-                float v[8];
-                const float4 b0 = ld_shared_f4(sbias + (c0 + q8 * 8) * 4);
-                const float4 b1 = ld_shared_f4(sbias + (c0 + q8 * 8 + 4) * 4);
-                v[0] = fmaf(__uint_as_float(r[q8 * 8]), alpha, b0.x);
-                v[1] = fmaf(__uint_as_float(r[q8 * 8 + 1]), alpha, b0.y);
-                v[2] = fmaf(__uint_as_float(r[q8 * 8 + 2]), alpha, b0.z);
-                v[3] = fmaf(__uint_as_float(r[q8 * 8 + 3]), alpha, b0.w);
-                v[4] = fmaf(__uint_as_float(r[q8 * 8 + 4]), alpha, b1.x);
-                v[5] = fmaf(__uint_as_float(r[q8 * 8 + 5]), alpha, b1.y);
-                v[6] = fmaf(__uint_as_float(r[q8 * 8 + 6]), alpha, b1.z);
-                v[7] = fmaf(__uint_as_float(r[q8 * 8 + 7]), alpha, b1.w);
-                if (rowadd_row != nullptr && valid && col_base + c0 + q8 * 8 < n_lim) {
-                  float rv[8];
-                  load8h(rowadd_row + col_base + c0 + q8 * 8, rv);
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) v[k] += rv[k];
-                }
-                if (act != PFD_ACT_NONE) {
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) v[k] = act_apply(v[k], act);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) h[q8 * 4 + k] = pack_h2(v[2 * k], v[2 * k + 1]);
-              }
-            }
-            const uint32_t slab = stg + i * 2048 + lane * 64;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t a = slab + ((k ^ sw64) << 4);
-              uint4 o = make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
-              if (has_res) o = hadd2x4(o, ld_shared_v4(a));
-              st_shared_v4(a, o.x, o.y, o.z, o.w);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) tma_store_4d(&p.tmO32, stg + i * 2048, col_base + c0, gx, gy, gn);
-          }
-          if (live16) {
-            const int c0 = cbeg + 32 * n32;
-            uint32_t r[16];
-            tmem_ld16(taddr + c0, r);
-            tmem_ld_wait();
-            uint32_t h[8];
-#pragma unroll
-            for (int q8 = 0; q8 < 2; ++q8) {
-              float v[8];
-              const float4 b0 = ld_shared_f4(sbias + (c0 + q8 * 8) * 4);
-              const float4 b1 = ld_shared_f4(sbias + (c0 + q8 * 8 + 4) * 4);
-              v[0] = fmaf(__uint_as_float(r[q8 * 8]), alpha, b0.x);
-              v[1] = fmaf(__uint_as_float(r[q8 * 8 + 1]), alpha, b0.y);
-              v[2] = fmaf(__uint_as_float(r[q8 * 8 + 2]), alpha, b0.z);
-              v[3] = fmaf(__uint_as_float(r[q8 * 8 + 3]), alpha, b0.w);
-              v[4] = fmaf(__uint_as_float(r[q8 * 8 + 4]), alpha, b1.x);
-              v[5] = fmaf(__uint_as_float(r[q8 * 8 + 5]), alpha, b1.y);
-              v[6] = fmaf(__uint_as_float(r[q8 * 8 + 6]), alpha, b1.z);
-              v[7] = fmaf(__uint_as_float(r[q8 * 8 + 7]), alpha, b1.w);
-              if (rowadd_row != nullptr && valid && col_base + c0 + q8 * 8 < n_lim) {
-                float rv[8];
-                load8h(rowadd_row + col_base + c0 + q8 * 8, rv);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] += rv[k];
-              }
-              if (act != PFD_ACT_NONE) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = act_apply(v[k], act);
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k) h[q8 * 4 + k] = pack_h2(v[2 * k], v[2 * k + 1]);
-            }
-            const uint32_t slab = stg + n32 * 2048 + lane * 32;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint32_t a = slab + ((k ^ sw32) << 4);
-              uint4 o = make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
-              if (has_res) o = hadd2x4(o, ld_shared_v4(a));
-              st_shared_v4(a, o.x, o.y, o.z, o.w);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) tma_store_4d(&p.tmO16, stg + n32 * 2048, col_base + c0, gx, gy, gn);
-          }
-          if (lane == 0) bulk_commit_group();
+          EpiTile e;
+          e.q = q; e.lane = lane; e.tx = tx; e.ty = ty; e.tn = tn; e.cbeg = cbeg; e.n32 = n32; e.tail16 = tail16;
+          e.col_base = col_base; e.n_lim = n_lim; e.has_res = has_res; e.valid = valid;
+          e.stg = stg; e.rbar = res_bar(warp - 2); e.tfull = tfull_bar(as); e.aph = aph; e.taddr = taddr; e.sbias = sbias;
+          e.alpha = alpha; e.act = act; e.rowadd_row = rowadd_row;
+          tma_store_epilogue<BN>(p, e, res_phase);
           tc_fence_before();
           mbar_arrive(tempty_bar(as));
           continue;
@@ -984,6 +1014,221 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair kernel
+// Same contraction on a PAIR of CTAs (cluster of two, tcgen05 cta_group::2): D[256 x BN] per pair, each CTA holding
+// its own 128 rows of A and HALF of the B tile (BN/2 weight rows) per K block -> per-SM operand ingest drops from
+// (128 + BN) x 128 B to (128 + BN/2) x 128 B per K block (BN = 256: 7.8 instead of 14 B per kFLOP), which is what the
+// 3x3 convs are bound by (r1/r2 ncu: 1.5 GB of L2->SM reads per launch at 10 TB/s with the tensor pipe 65-78 % busy).
+// Protocol (both CTAs run every role, identical shared-memory layouts):
+//   producer  (warp 0, each CTA): waits its OWN empty barrier, loads its A tile and its B half with the cta_group::2
+//             form of cp.async.bulk.tensor, whose bytes complete on the LEADER's full barrier; the leader's producer
+//             arms that barrier with the bytes of both CTAs;
+//   MMA       (warp 1 of the leader = cluster rank 0 only): tcgen05.mma.cta_group::2 (M = 256), tcgen05.commit with
+//             cluster multicast releases the stage in both CTAs and publishes the accumulator to both epilogues;
+//   epilogue  (warps 2..9, each CTA): TMA-store epilogue on the CTA's own 128 x BN accumulator in its own TMEM; one lane
+//             per warp arrives on the LEADER's tmem_empty barrier (16 arrivals per tile).
+// Only the TMA-store epilogue exists here (plain channel-last outputs, no GEGLU / split-K / batched B).
+template <int BN>
+struct GemmCfg2 {
+  static constexpr int STAGE_B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
+  static constexpr int WARP_STG = epi_stg_bytes(BN, true);
+  static constexpr int FIXED = 1024 + 1024 + EPI_WARPS * WARP_STG + 2 * BN * 4;
+  static constexpr int RAW_STAGES = (SMEM_BUDGET - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = RAW_STAGES > 8 ? 8 : RAW_STAGES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128u : (2 * BN <= 256 ? 256u : 512u);
+  static_assert(STAGE_B_BYTES % 1024 == 0, "B half stage must keep 1024-B swizzle alignment");
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N constraint for M = 256");
+  static_assert(STAGES >= 3, "too few pipeline stages");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg2<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const uint32_t smemA = base;
+  const uint32_t smemB = base + STAGES * STAGE_A_BYTES;
+  const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  auto res_bar = [&](int w) { return bars + 8u * (2 * STAGES + 5 + w); };
+  volatile uint32_t* tmem_slot_g =
+      reinterpret_cast<volatile uint32_t*>(gbase + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmO32);
+    tma_prefetch_desc(&p.tmO16);
+    if (p.residual) {
+      tma_prefetch_desc(&p.tmR32);
+      tma_prefetch_desc(&p.tmR16);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * EPI_WARPS);       // one lane per epilogue warp of both CTAs
+    }
+    for (int w = 0; w < EPI_WARPS; ++w) mbar_init(res_bar(w), 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();            // barriers of BOTH CTAs are initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_g;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_nb;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int total_work = m_pairs * p.n_tiles;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = cluster_id; work < total_work; work += n_clusters) {
+        const int n_tile = work % p.n_tiles;
+        const int m_tile = 2 * (work / p.n_tiles) + (int)rank;     // may be == m_tiles (odd tail): fully out of raster
+        const int tx = m_tile % p.tiles_w;
+        const int ty = (m_tile / p.tiles_w) % p.tiles_h;
+        const int tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int x0 = tx * p.bw * p.stride;
+        const int y0 = ty * p.bh * p.stride;
+        const int n0 = tn * p.bn;
+        int kofs = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int ntap = p.taps[s];
+          for (int t = 0; t < ntap; ++t) {
+            const int dy = (ntap == 9) ? (t / 3 - 1 + p.tap_off) : 0;
+            const int dx = (ntap == 9) ? (t % 3 - 1 + p.tap_off) : 0;
+            for (int j = 0; j < p.chunks[s]; ++j) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_pair(smemA + stage * STAGE_A_BYTES, &p.tmA[s], full_bar(stage), j * BK, x0 + dx, y0 + dy, n0);
+              tma_load_3d_pair(smemB + stage * Cfg::STAGE_B_BYTES, &p.tmB, full_bar(stage), kofs + j * BK,
+                               n_tile * BN + (int)rank * (BN / 2), 0);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+            kofs += p.a_c[s];
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16_pair(BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int work = cluster_id; work < total_work; work += n_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_kmajor_desc(smemA + stage * STAGE_A_BYTES);
+          const uint64_t bdesc = make_sw128_kmajor_desc(smemB + stage * Cfg::STAGE_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_pair(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(empty_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_pair(tfull_bar(as));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+    const int q = warp & 3;
+    const int half_id = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int rdx = row % p.bw;
+    const int rdy = (row / p.bw) % p.bh;
+    const int rdn = row / (p.bw * p.bh);
+    constexpr int nch = BN / 16;
+    const int ch_begin = half_id == 0 ? 0 : (nch + 1) / 2;
+    const int ch_end = half_id == 0 ? (nch + 1) / 2 : nch;
+    const int cbeg = ch_begin * 16, cend = ch_end * 16;
+    const uint32_t fixed0 = base + STAGES * Cfg::STAGE_BYTES + 1024;
+    uint32_t res_phase = 0;
+    int it = 0;
+    for (int work = cluster_id; work < total_work; work += n_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int n_tile = work % p.n_tiles;
+      const int m_tile = 2 * (work / p.n_tiles) + (int)rank;
+      EpiTile e;
+      e.q = q; e.lane = lane;
+      e.tx = m_tile % p.tiles_w;
+      e.ty = (m_tile / p.tiles_w) % p.tiles_h;
+      e.tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int x = e.tx * p.bw + rdx, y = e.ty * p.bh + rdy, n = e.tn * p.bn + rdn;
+      e.valid = (x < p.W) && (y < p.H) && (n < p.NB);
+      e.cbeg = cbeg; e.n32 = (cend - cbeg) >> 5; e.tail16 = ((cend - cbeg) & 16) != 0;
+      e.col_base = n_tile * BN; e.n_lim = p.N;
+      e.has_res = p.residual != nullptr;
+      e.stg = fixed0 + (warp - 2) * Cfg::WARP_STG;
+      e.rbar = res_bar(warp - 2);
+      e.tfull = tfull_bar(as);
+      e.aph = aph;
+      e.taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      e.sbias = fixed0 + EPI_WARPS * Cfg::WARP_STG + as * (BN * 4);
+      e.alpha = p.alpha; e.act = p.act;
+      e.rowadd_row = (p.rowadd && e.valid) ? p.rowadd + (long long)n * p.rowadd_ld : nullptr;
+      const int et = threadIdx.x - 64;
+      if (et < BN) {
+        const int c = e.col_base + et;
+        const float b = (p.bias != nullptr && c < p.N) ? __half2float(__ldg(p.bias + c)) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(e.sbias + et * 4), "f"(b) : "memory");
+      }
+      tma_store_epilogue<BN>(p, e, res_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();            // neither CTA may leave (or free TMEM) while the pair's MMAs / remote arrives are in flight
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // Split-K second pass: sum the fp32 partials of all splits and apply the fused epilogue
 // (bias, per-image row add, activation, residual) with the same generic output addressing.
 __global__ void __launch_bounds__(256)
@@ -1205,6 +1450,29 @@ static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream, const pfd_g
   return lean ? launch_gemm_t<BN, true, false>(p, grid, stream) : launch_gemm_t<BN, false, false>(p, grid, stream);
 }
 
+template <int BN>
+static int launch_gemm_pair(GemmParams& p, int clusters, cudaStream_t stream, const pfd_gemm_desc* d) {
+  using Cfg = GemmCfg2<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm pair BN=%d): %s", BN, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  if (int rc = encode_epilogue_maps(p, d)) return rc;
+  static int trace = -1;
+  if (trace < 0) {
+    const char* e = getenv("PFD_GEMM_TRACE");
+    trace = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (trace)
+    fprintf(stderr, "GEMMTRACE M=%lld N=%d K=%d nseg=%d taps=%d stride=%d act=%d bias=%d res=%d rowadd=%d BN=%d lean=P "
+            "splits=1 grid=%d batched=0 vec=1 plain=1 tmae=2\n", (long long)p.W * p.H * p.NB, p.N, p.num_kb * BK, p.nseg,
+            p.taps[0], p.stride, p.act, p.bias != nullptr, p.residual != nullptr, p.rowadd != nullptr, BN, 2 * clusters);
+  launch_k(gemm_tc2_kernel<BN>, dim3(2 * clusters), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
+  return check_launch("pfd_gemm_f16(pair)");
+}
+
 }  // namespace pfd
 
 using namespace pfd;
@@ -1299,6 +1567,34 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   p.n_tiles = (int)cdivll(d->N, BNsel);
   p.splits = 1;
 
+  // ---- CTA-pair kernel (cta_group::2, 256 x BN per pair): long-K contractions with a plain channel-last output whose
+  //      operand ingest, not the epilogue, is the bound (3x3 convs, K >= 1024 Linears) and that fill the 74 pairs
+  int k_blocks = 0;
+  for (int s = 0; s < d->nseg; ++s) k_blocks += d->taps[s] * ((d->a_c[s] + BK - 1) / BK);
+  const int pair_mode = option("gemm_pair", 0);
+  bool use_pair = pair_mode > 0 && !geglu && !p.b_batched && !d->bn_force && p.vec_ok && p.cdiv >= p.N && p.ndiv == 1 &&
+                  gemm_lean_enabled() && (d->H == 1 || d->so_y >= (long long)d->so_x * d->W) &&
+                  (d->NB == 1 || d->so_n1 > 0) && m_tiles >= 2 && k_blocks >= (pair_mode > 1 ? 1 : 16);
+  if (use_pair) {
+    const long long m_pairs = (m_tiles + 1) / 2;
+    const int pc[3] = {256, 160, 128};
+    double pbest = -1;
+    int pbn = 160;
+    for (int i = 0; i < 3; ++i) {
+      const long long tiles = m_pairs * cdivll(d->N, pc[i]);
+      const double cost = (double)cdivll(tiles, sms / 2) * (pc[i] + 24);
+      if (pbest < 0 || cost < pbest - 1e-9) {
+        pbest = cost; pbn = pc[i];
+      }
+    }
+    // the machine must be filled: at least one full wave of pairs (smaller problems keep split-K / the single-CTA tiles)
+    if (m_pairs * cdivll(d->N, pbn) * 2 < sms && pair_mode < 2) use_pair = false;
+    else {
+      BNsel = pbn;
+      p.n_tiles = (int)cdivll(d->N, BNsel);
+    }
+  }
+
   // ---- tensor maps
   int num_kb = 0;
   for (int s = 0; s < d->nseg; ++s) {
@@ -1318,7 +1614,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
   float* const skws = splitk_workspace(st);     // allocated by the first eager call on this device
   // ---- split-K for long-K problems that cannot fill the machine (8x8-level convs): fewer, wider N tiles
   //      (less A re-read through L2) x several K slices, fp32 partials reduced by splitk_finish_kernel.
-  if (!geglu && !d->bn_force && num_kb >= 32) {
+  if (!use_pair && !geglu && !d->bn_force && num_kb >= 32) {
     int bn_sk = 128;
     const int sk_cands[4] = {256, 192, 160, 128};
     for (int i = 0; i < 4; ++i)
@@ -1351,9 +1647,18 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
     cuuint64_t dims[3] = {(cuuint64_t)d->K, (cuuint64_t)d->N, (cuuint64_t)nbatch};
     const long long bs = p.b_batched ? d->b_batch_stride : (long long)d->K * d->N;
     cuuint64_t strides[2] = {(cuuint64_t)d->K * 2, (cuuint64_t)bs * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BNsel, 1};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(use_pair ? BNsel / 2 : BNsel), 1};   // pair: each CTA loads half
     cuuint32_t estr[3] = {1, 1, 1};
     if (int rc = encode_map(&p.tmB, d->b_ptr, 3, dims, strides, box, estr, "B")) return rc;
+  }
+  if (use_pair) {
+    const long long work = ((m_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = (int)(work < sms / 2 ? work : sms / 2);
+    switch (BNsel) {
+      case 128: return launch_gemm_pair<128>(p, clusters, st, d);
+      case 160: return launch_gemm_pair<160>(p, clusters, st, d);
+      default: return launch_gemm_pair<256>(p, clusters, st, d);
+    }
   }
 
   const long long total = m_tiles * p.n_tiles * p.splits;

@@ -56,35 +56,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// Same with a compile-time suspend hint (HINT_NS = 0: no hint operand, the hardware's default short time limit) - for
-// kernels whose barrier hand-offs sit on the critical path (every wake-up latency is exposed).
-template <uint32_t HINT_NS>
-__device__ __forceinline__ void mbar_wait_h(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    if constexpr (HINT_NS == 0) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(bar), "r"(parity)
-          : "memory");
-    } else {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(bar), "r"(parity), "r"(HINT_NS)
-          : "memory");
-    }
-    if (ok) return;
-    if (++spins > (1u << 26)) asm volatile("trap;");
-  }
-}
-
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

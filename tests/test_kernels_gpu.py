@@ -128,6 +128,62 @@ def test_gemm_tma_store_epilogue_bit_exact(nv, case):
     assert torch.equal(out0, out1), f"TMA-store epilogue differs from the register epilogue: max |d| = {(out0.float() - out1.float()).abs().max().item()}"
 
 
+@pytest.mark.parametrize("case", ["conv_res_2tiles", "conv_many_waves", "conv_wide_rowadd_silu", "linear_odd_ragged",
+                                  "conv_stride2", "conv_tiny", "conv_skip_segments"])
+def test_gemm_cta_pair(nv, case):
+    """CTA-pair kernel (cluster of two, tcgen05 cta_group::2: M = 256 across the pair, B split between the two CTAs,
+    cta_group::2 TMA loads completing on the leader's barrier, multicast commits, remote tmem_empty arrives) against
+    torch fp32 and against the single-CTA kernel on the same operands.  Cases: one / many tiles per cluster (accumulator
+    double buffering and pipeline phases across tiles), BN = 256 / 160 / 128, an ODD number of 128-row tiles (the
+    second CTA of the last pair works on a tile that is completely outside the raster), N not a multiple of the
+    tile, stride 2, per-image row add + SiLU, residual, extra 1x1 K segments."""
+    def run():
+        if case == "linear_odd_ragged":
+            x, w, r = rnd(640, 1024), rnd(1288, 1024, scale=1024 ** -0.5, seed=1), rnd(640, 1288, seed=3)
+            return nv.linear(x, w, None, residual=r), x.float() @ w.float().t() + r.float()
+        NB, H, W, C, N = {"conv_res_2tiles": (2, 64, 64, 320, 320), "conv_many_waves": (8, 64, 64, 128, 320),
+                          "conv_wide_rowadd_silu": (2, 32, 32, 128, 1280), "conv_stride2": (4, 32, 32, 128, 256),
+                          "conv_tiny": (3, 8, 8, 128, 128), "conv_skip_segments": (2, 32, 32, 64, 160)}[case]
+        x = rnd(NB, H, W, C)
+        w4 = rnd(N, C, 3, 3, scale=(9 * C) ** -0.5, seed=1)
+        b = rnd(N, seed=2)
+        wp = w4.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+        xr = x.float().permute(0, 3, 1, 2)
+        if case == "conv_stride2":
+            out = nv.conv3x3(x, wp, b, stride=2)
+            ref = F.conv2d(xr, w4.float(), b.float(), stride=2, padding=1)
+        elif case == "conv_wide_rowadd_silu":
+            ra = rnd(NB, N, seed=5)
+            out = nv.conv3x3(x, wp, b, rowadd=ra, act=nv.ACT_SILU)
+            ref = F.silu(F.conv2d(xr, w4.float(), b.float(), padding=1) + ra.float()[:, :, None, None])
+        elif case == "conv_skip_segments":
+            s1, s2 = rnd(NB, H, W, 96, seed=7), rnd(NB, H, W, 32, seed=8)
+            ws = rnd(N, 128, scale=128 ** -0.5, seed=9)
+            out = nv.conv3x3(x, torch.cat([wp, ws], 1).contiguous(), b, skip=[s1, s2])
+            ref = F.conv2d(xr, w4.float(), b.float(), padding=1) + \
+                F.conv2d(torch.cat([s1, s2], 3).float().permute(0, 3, 1, 2), ws.float()[:, :, None, None])
+        else:
+            r = rnd(NB, H, W, N, seed=3)
+            out = nv.conv3x3(x, wp, b, residual=r)
+            ref = F.conv2d(xr, w4.float(), b.float(), padding=1) + r.float().permute(0, 3, 1, 2)
+        return out, ref.permute(0, 2, 3, 1)
+    nv.set_env_option(None, None)
+    try:
+        nv.set_env_option("gemm_pair", 0)
+        out0, ref = run()
+        out0 = out0.clone()
+        nv.set_env_option("gemm_pair", 2)          # 2 = force the pair kernel wherever it is applicable
+        out1, _ = run()
+        torch.cuda.synchronize()
+    finally:
+        nv.set_env_option(None, None)
+    close(out0, ref)
+    close(out1, ref)
+    dmax = (out0.float() - out1.float()).abs().max().item()
+    print(f"[cta pair] {case}: max |pair - single| = {dmax:.3e}")
+    assert dmax <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("C", [64, 320])
 def test_geglu(nv, C):
     M, inner = 512, 4 * C

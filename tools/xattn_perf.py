@@ -47,8 +47,7 @@ def main():
         out = torch.empty(B, Nq, H * d, device=dev, dtype=torch.float16)
         run = lambda: nv.flash_attn(q, k, vt, B=B, heads=H, Nq=Nq, Nk=Nk, scale=d ** -0.5, out=out)
         variants = {"generic": {"xattn_short": 0}, "short": {}, "short poly/4": {"flash_poly_mod": 4},
-                    "short hint 256": {"xattn_wait_hint": 256}, "short hint 32": {"xattn_wait_hint": 32},
-                    "short no hint": {"xattn_wait_hint": 0}}
+                    "generic poly/4": {"xattn_short": 0, "flash_poly_mod": 4}}
         if not (Nk <= 160 and d <= 48):
             variants = {"generic": {}, "generic poly/4": {"flash_poly_mod": 4}, "generic poly/3": {"flash_poly_mod": 3},
                         "generic poly/2": {"flash_poly_mod": 2}}
