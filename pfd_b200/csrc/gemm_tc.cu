@@ -57,6 +57,11 @@ struct alignas(64) GemmParams {
   int splits;        // split-K factor (1 = off); work items = tiles * splits
   int kb_per_split;
   float* ws;         // fp32 partials [splits][m_tiles*128][N] when splits > 1
+  // stream-K tail (single-CTA kernel, TMA-store epilogue): tiles < sk_dp_tiles are processed whole, one per CTA per
+  // wave; the K blocks of the remaining sk_R tiles are spread evenly over ALL CTAs (see gemm_work)
+  int sk_dp_tiles, sk_R;
+  float* sk_ws;      // fp32 partial tiles [2 * grid][128][BN]
+  int* sk_flags;     // [2 * grid] 0 / 1, reset by the consumer
   float alpha;
   int act;
   const __half* bias;
@@ -166,6 +171,65 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// One unit of work of a persistent CTA: K blocks [kb0, kb1) of output tile `tile`.
+//   mode 0: the whole contraction of the tile (or, with split-K, slice `slot`) -> normal epilogue
+//   mode 1: stream-K contributor: raw fp32 partial tile -> sk_ws[slot], then sk_flags[slot] = 1
+//   mode 2: stream-K owner (its range ends with the tile's last K block): adds the contributors' partials, normal epilogue
+// Stream-K tail: with T tiles on G CTAs the last wave holds R = T mod G tiles (every UNet conv: 0.46 or 0.73 or 0.86 of a
+// wave, i.e. 13.5 % of the machine idle on average).  Their R * num_kb K blocks are cut into G equal contiguous ranges;
+// a range covers the tail of one tile (processed LAST: this CTA owns that tile if it reaches its end) and possibly the
+// head of the next (processed FIRST: a pure contributor that depends on nobody, so its partial is published early and
+// the owner - the next CTA - rarely waits).
+struct WorkItem {
+  int tile, kb0, kb1, mode, slot;
+};
+__device__ __forceinline__ void sk_range(const GemmParams& p, int c, int G, int& u0, int& u1) {
+  const long long U = (long long)p.sk_R * p.num_kb;
+  u0 = (int)(U * c / G);
+  u1 = (int)(U * (c + 1) / G);
+}
+__device__ __forceinline__ bool gemm_work(const GemmParams& p, int wi, int total_tiles, WorkItem& w) {
+  const int G = gridDim.x, c = blockIdx.x;
+  if (p.sk_R == 0) {
+    const int work = c + wi * G;
+    if (work >= total_tiles * p.splits) return false;
+    w.tile = work % total_tiles;
+    w.slot = work / total_tiles;
+    w.kb0 = w.slot * p.kb_per_split;
+    w.kb1 = min(p.num_kb, w.kb0 + p.kb_per_split);
+    w.mode = 0;
+    return true;
+  }
+  // The stream-K segments come FIRST and the whole tiles after them: the contributor -> flag -> owner hand-off
+  // (MMA of the segment + partial store + release visibility + gather, ~10 us) is then hidden behind the whole
+  // tiles of the same CTA (the accumulator is double-buffered, the MMA warp runs ahead of a waiting epilogue) and the
+  // kernel ends with perfectly balanced whole tiles.  (Segments LAST measured 0.84-0.98x: the hand-off chain alone is
+  // as long as a tile.)
+  int u0, u1;
+  sk_range(p, c, G, u0, u1);
+  const int KB = p.num_kb;
+  const int t0 = u0 / KB;
+  const int aend = min(u1, (t0 + 1) * KB);
+  const bool has_b = u1 > aend;                        // the range spills into tile t0 + 1
+  const int nseg = (u1 > u0) ? (has_b ? 2 : 1) : 0;
+  if (wi >= nseg) {
+    const int n_dp = p.sk_dp_tiles / G;                // whole waves
+    if (wi - nseg >= n_dp) return false;
+    w.tile = c + (wi - nseg) * G; w.kb0 = 0; w.kb1 = p.num_kb; w.mode = 0; w.slot = 0;
+    return true;
+  }
+  const int seg = wi;
+  int s0, s1, t;
+  if (seg == 0 && has_b) { s0 = aend; s1 = u1; t = t0 + 1; }
+  else { s0 = u0; s1 = aend; t = t0; }
+  w.tile = p.sk_dp_tiles + t;
+  w.kb0 = s0 - t * KB;
+  w.kb1 = s1 - t * KB;
+  w.mode = (w.kb1 == KB) ? (w.kb0 == 0 ? 0 : 2) : 1;
+  w.slot = 2 * c + ((seg == 0 && has_b) ? 1 : 0);
+  return true;
+}
+
 // Per-warp view of one output tile for the TMA-store epilogue (shared by the single-CTA and the CTA-pair kernel).
 struct EpiTile {
   int q, lane;                 // TMEM lane quarter / lane of the warp
@@ -178,7 +242,19 @@ struct EpiTile {
   float alpha;
   int act;
   const __half* rowadd_row;
+  int sk_mode, sk_slot;        // stream-K: WorkItem::mode / slot (0 / unused for whole tiles)
+  int sk_t, sk_kb0;            // stream-K owner: index of the tile in the tail, first K block of its own range
+  int stg_warp;                // index of this epilogue warp (0..7)
 };
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* ptr, int v) {
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
 
 // ---------------- TMA-store epilogue.  This warp owns rows [32q, 32q+32) x columns [cbeg, cend) of the tile
 // and a private staging area holding that share as slabs of 32 rows x 32 columns (2 KB, SWIZZLE_64B) plus at
@@ -205,6 +281,61 @@ __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const Ep
   for (int i = 0; i < n32; ++i) live32 += (col_base + cbeg + 32 * i < n_lim) ? 1 : 0;
   const bool live16 = tail16 && (col_base + cbeg + 32 * n32 < n_lim);
   const uint32_t rb_addr = e.rbar;
+  if (e.sk_mode == 1) {
+    // ---- stream-K contributor: raw fp32 accumulators of this CTA's K range -> sk_ws[slot][row][col], then publish
+    // partial-tile layout: private to the (contributor warp, owner warp) pair that share a tile position, so it is chosen
+    // for the memory system, not for humans: [slot][warp][16-byte group g of the warp's columns][lane] -> every
+    // warp-wide store / load is one contiguous 512-byte request (the row-major version cost 6 + 12 us per tile)
+    uint4* pw = reinterpret_cast<uint4*>(p.sk_ws) + ((long long)e.sk_slot * EPI_WARPS + (e.stg_warp)) * (BN / 8) * 32 + lane;
+    mbar_wait(e.tfull, e.aph);
+    tc_fence_after();
+    for (int i = 0; i < live32; ++i) {
+      const int c0 = cbeg + 32 * i;
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int v4 = 0; v4 < 8; ++v4)
+        __stcg(pw + (i * 8 + v4) * 32, make_uint4(r[4 * v4], r[4 * v4 + 1], r[4 * v4 + 2], r[4 * v4 + 3]));
+    }
+    if (live16) {
+      const int c0 = cbeg + 32 * n32;
+      uint32_t r[16];
+      tmem_ld16(taddr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4)
+        __stcg(pw + (n32 * 8 + v4) * 32, make_uint4(r[4 * v4], r[4 * v4 + 1], r[4 * v4 + 2], r[4 * v4 + 3]));
+    }
+    __threadfence();
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // every epilogue thread's partial rows are written and fenced
+    if (threadIdx.x == 64) st_release_gpu(p.sk_flags + e.sk_slot, 1);
+    return;
+  }
+  // stream-K owner: the CTAs whose ranges cover K blocks [0, sk_kb0) of this tile; their partial tiles are added to the
+  // accumulator before the normal epilogue.  Contributor cc used slot 2cc if its range STARTS inside this tile
+  // (its tail part) and slot 2cc + 1 if it spilled over from the previous tile (its head part).
+  int nsrc = 0, src_slot[6];
+  if (e.sk_mode == 2) {
+    const int G = gridDim.x;
+    const int tstart = e.sk_t * p.num_kb;
+    for (int cc = (int)blockIdx.x - 1; cc >= 0 && nsrc < 6; --cc) {
+      int u0, u1;
+      sk_range(p, cc, G, u0, u1);
+      if (u1 <= tstart) break;
+      if (u1 > u0) src_slot[nsrc++] = (u0 >= tstart) ? 2 * cc : 2 * cc + 1;
+    }
+    if (threadIdx.x == 64) {
+      for (int j = 0; j < nsrc; ++j) {
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(p.sk_flags + src_slot[j]) == 0) {
+          __nanosleep(64);
+          if (++spins > (1u << 24)) asm volatile("trap;");
+        }
+        p.sk_flags[src_slot[j]] = 0;                       // consumed: ready for the next launch
+      }
+    }
+  }
   if (lane == 0) {
     bulk_wait_read_all();                         // stores of the previous tile have read the slabs
     if (has_res && (live32 > 0 || live16)) {
@@ -228,6 +359,18 @@ __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const Ep
     uint32_t r[32];
     tmem_ld32(taddr + c0, r);
     tmem_ld_wait();
+    for (int j = 0; j < nsrc; ++j) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.sk_ws) +
+                         (((long long)src_slot[j] * EPI_WARPS + e.stg_warp) * (BN / 8) + i * 8) * 32 + lane;
+#pragma unroll
+      for (int v4 = 0; v4 < 8; ++v4) {
+        const uint4 u = __ldcg(src + v4 * 32);
+        r[4 * v4] = __float_as_uint(__uint_as_float(r[4 * v4]) + __uint_as_float(u.x));
+        r[4 * v4 + 1] = __float_as_uint(__uint_as_float(r[4 * v4 + 1]) + __uint_as_float(u.y));
+        r[4 * v4 + 2] = __float_as_uint(__uint_as_float(r[4 * v4 + 2]) + __uint_as_float(u.z));
+        r[4 * v4 + 3] = __float_as_uint(__uint_as_float(r[4 * v4 + 3]) + __uint_as_float(u.w));
+      }
+    }
     uint32_t h[16];
     if (rowadd_row == nullptr && act == PFD_ACT_NONE) {
 #pragma unroll
@@ -281,6 +424,18 @@ __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const Ep
     uint32_t r[16];
     tmem_ld16(taddr + c0, r);
     tmem_ld_wait();
+    for (int j = 0; j < nsrc; ++j) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.sk_ws) +
+                         (((long long)src_slot[j] * EPI_WARPS + e.stg_warp) * (BN / 8) + n32 * 8) * 32 + lane;
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        const uint4 u = __ldcg(src + v4 * 32);
+        r[4 * v4] = __float_as_uint(__uint_as_float(r[4 * v4]) + __uint_as_float(u.x));
+        r[4 * v4 + 1] = __float_as_uint(__uint_as_float(r[4 * v4 + 1]) + __uint_as_float(u.y));
+        r[4 * v4 + 2] = __float_as_uint(__uint_as_float(r[4 * v4 + 2]) + __uint_as_float(u.z));
+        r[4 * v4 + 3] = __float_as_uint(__uint_as_float(r[4 * v4 + 3]) + __uint_as_float(u.w));
+      }
+    }
     uint32_t h[8];
 #pragma unroll
     for (int q8 = 0; q8 < 2; ++q8) {
@@ -392,18 +547,16 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_nb;
   const int total_tiles = m_tiles * p.n_tiles;
-  const int total_work = total_tiles * p.splits;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-        const int tile = work % total_tiles;
-        const int split = work / total_tiles;
-        const int kb_begin = split * p.kb_per_split;
-        const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+      WorkItem w;
+      for (int wi = 0; gemm_work(p, wi, total_tiles, w); ++wi) {
+        const int tile = w.tile;
+        const int kb_begin = w.kb0, kb_end = w.kb1;
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int tx = m_tile % p.tiles_w;
@@ -444,12 +597,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       constexpr uint32_t idesc = make_idesc_f16(BN);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+      WorkItem w;
+      for (int it = 0; gemm_work(p, it, total_tiles, w); ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
-        const int kb_begin = (work / total_tiles) * p.kb_per_split;
-        const int nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
+        const int nkb = w.kb1 - w.kb0;
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -493,10 +645,10 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const int ch_end = half_id == 0 ? (nch + 1) / 2 : nch;
     const bool plain_cols = p.cdiv >= p.N;  // no head split: column offset = col * so_c0
     uint32_t res_phase = 0;                 // TMAE: parity of this warp's residual barrier
-    int it = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
-      const int tile = work % total_tiles;
-      const int split = work / total_tiles;
+    WorkItem w;
+    for (int it = 0; gemm_work(p, it, total_tiles, w); ++it) {
+      const int tile = w.tile;
+      const int split = w.slot;
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int n_tile = tile % p.n_tiles;
@@ -631,6 +783,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           e.col_base = col_base; e.n_lim = n_lim; e.has_res = has_res; e.valid = valid;
           e.stg = stg; e.rbar = res_bar(warp - 2); e.tfull = tfull_bar(as); e.aph = aph; e.taddr = taddr; e.sbias = sbias;
           e.alpha = alpha; e.act = act; e.rowadd_row = rowadd_row;
+          e.sk_mode = w.mode; e.sk_slot = w.slot; e.sk_t = w.tile - p.sk_dp_tiles; e.sk_kb0 = w.kb0; e.stg_warp = warp - 2;
           tma_store_epilogue<BN>(p, e, res_phase);
           tc_fence_before();
           mbar_arrive(tempty_bar(as));
@@ -1207,6 +1360,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
       e.sbias = fixed0 + EPI_WARPS * Cfg::WARP_STG + as * (BN * 4);
       e.alpha = p.alpha; e.act = p.act;
       e.rowadd_row = (p.rowadd && e.valid) ? p.rowadd + (long long)n * p.rowadd_ld : nullptr;
+      e.sk_mode = 0; e.sk_slot = 0; e.sk_t = 0; e.sk_kb0 = 0; e.stg_warp = warp - 2;
       const int et = threadIdx.x - 64;
       if (et < BN) {
         const int c = e.col_base + et;
@@ -1305,6 +1459,7 @@ splitk_finish_kernel(const __grid_constant__ GemmParams p) {
 
 // ------------------------------------------------------------------------------------------ host
 constexpr size_t SPLITK_WS_BYTES = 64ull << 20;
+constexpr size_t SK_FLAG_BYTES = 4096;          // stream-K flags live at the end of the workspace
 // One fp32 split-K workspace per DEVICE, allocated by the first pfd_gemm_f16 call on that device that is not
 // inside a stream capture (cudaMalloc is illegal while capturing) - i.e. in the eager warm-up pass that every
 // graph-captured path of this package runs first - and then shared by the eager and the captured launches, so
@@ -1328,6 +1483,13 @@ static float* splitk_workspace(cudaStream_t st) {
   float* pnew = nullptr;
   if (cudaMalloc(&pnew, SPLITK_WS_BYTES) != cudaSuccess) {
     (void)cudaGetLastError();
+    return nullptr;
+  }
+  // the last SK_FLAG_BYTES hold the stream-K ready flags: zero once, every consumer resets the flags it has read
+  if (cudaMemset(reinterpret_cast<char*>(pnew) + SPLITK_WS_BYTES - SK_FLAG_BYTES, 0, SK_FLAG_BYTES) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(pnew);
     return nullptr;
   }
   ws[dev] = pnew;
@@ -1433,6 +1595,28 @@ static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream, const pfd_g
       tmae = false;                       // raster not expressible as a tensor map: keep the register epilogue
       g_last_error.clear();
     }
+    // stream-K tail (see gemm_work), OPT-IN (gemm_streamk = 1): the tiles of the last, partially filled wave are spread
+    // over all SMs by K range; every tile of the tail must be covered by at most 6 contributors.  Correct and
+    // deterministic, but measured 0.84-0.99x on the UNet's convs / long-K Linears (profiles/r2_ab_gemm_streamk.log): the
+    // per-CTA cost of the hand-off (contributor epilogue + release visibility + gather + two extra pipeline fills,
+    // ~10 us) is as large as the 0.14-0.54 tile it saves at these tile times (13-45 us).
+    p.sk_R = 0;
+    p.sk_dp_tiles = 0;
+    if (tmae && option("gemm_streamk", 0)) {
+      const int G = num_sms();
+      const long long T = (long long)p.tiles_w * p.tiles_h * p.tiles_nb * p.n_tiles;
+      const long long R = T % G, waves = (T + G - 1) / G;
+      float* ws = splitk_workspace(stream);
+      const size_t need = (size_t)2 * G * BM * BN * sizeof(float);
+      if (ws && R > 0 && p.num_kb >= 16 && R * 6 >= G && (size_t)2 * G * sizeof(int) <= SK_FLAG_BYTES &&
+          need <= SPLITK_WS_BYTES - SK_FLAG_BYTES && (double)T / G < 0.95 * (double)waves) {
+        p.sk_dp_tiles = (int)(T - R);
+        p.sk_R = (int)R;
+        p.sk_ws = ws;
+        p.sk_flags = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + SPLITK_WS_BYTES - SK_FLAG_BYTES);
+        grid = G;
+      }
+    }
   }
   static int trace = -1;
   if (trace < 0) {
@@ -1441,9 +1625,9 @@ static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream, const pfd_g
   }
   if (trace)   // one line per launch, joined with an ncu launch list by tools/gemm_breakdown.py
     fprintf(stderr, "GEMMTRACE M=%lld N=%d K=%d nseg=%d taps=%d stride=%d act=%d bias=%d res=%d rowadd=%d BN=%d lean=%d "
-            "splits=%d grid=%d batched=%d vec=%d plain=%d tmae=%d\n", (long long)p.W * p.H * p.NB, p.N, p.num_kb * BK, p.nseg,
+            "splits=%d grid=%d batched=%d vec=%d plain=%d tmae=%d sk=%d\n", (long long)p.W * p.H * p.NB, p.N, p.num_kb * BK, p.nseg,
             p.taps[0], p.stride, p.act, p.bias != nullptr, p.residual != nullptr, p.rowadd != nullptr, BN, (int)lean,
-            p.splits, grid, p.b_batched, p.vec_ok, (int)(p.cdiv >= p.N), (int)tmae);
+            p.splits, grid, p.b_batched, p.vec_ok, (int)(p.cdiv >= p.N), (int)tmae, p.sk_R);
   if constexpr (BN <= 192) {
     if (tmae) return launch_gemm_t<BN, true, true>(p, grid, stream);
   }
@@ -1629,7 +1813,7 @@ extern "C" PFD_API int pfd_gemm_f16(const pfd_gemm_desc* d) {
       if (splits > 8) splits = 8;
       if (splits > num_kb / 8) splits = num_kb / 8;
       const size_t need = (size_t)splits * (size_t)m_tiles * BM * (size_t)d->N * sizeof(float);
-      if (splits >= 2 && need <= SPLITK_WS_BYTES) {
+      if (splits >= 2 && need <= SPLITK_WS_BYTES - SK_FLAG_BYTES) {
         float* ws = skws;
         if (ws) {
           BNsel = bn_sk;

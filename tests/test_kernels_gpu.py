@@ -117,13 +117,15 @@ def test_gemm_tma_store_epilogue_bit_exact(nv, case):
         return s_, torch.bmm(q.float(), k.float().transpose(1, 2))
     nv.set_env_option(None, None)
     try:
+        nv.set_env_option("gemm_streamk", 0)        # the stream-K tail changes the fp32 summation order (own test below)
         nv.set_env_option("gemm_tma_epi", 0)
         out0, ref = run()
         out0 = out0.clone()
+        nv.set_env_option("gemm_tma_epi", 1)
+        out1, _ = run()
+        torch.cuda.synchronize()
     finally:
         nv.set_env_option(None, None)
-    out1, _ = run()
-    torch.cuda.synchronize()
     close(out0, ref)
     assert torch.equal(out0, out1), f"TMA-store epilogue differs from the register epilogue: max |d| = {(out0.float() - out1.float()).abs().max().item()}"
 
@@ -182,6 +184,60 @@ def test_gemm_cta_pair(nv, case):
     dmax = (out0.float() - out1.float()).abs().max().item()
     print(f"[cta pair] {case}: max |pair - single| = {dmax:.3e}")
     assert dmax <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("case", ["conv_l1", "conv_l2_single_wave", "conv_l0_res", "linear_bigk_res", "conv_ragged_rowadd_silu"])
+def test_gemm_stream_k_tail(nv, case):
+    """Stream-K tail of the persistent GEMM: the tiles of the last, partially filled wave are cut into K ranges over ALL
+    SMs (contributors publish fp32 partial tiles through the workspace + a ready flag, the CTA that reaches the tile's
+    last K block adds them and runs the normal TMA-store epilogue).  Against torch fp32 and against the plain tiling
+    (gemm_streamk = 0; only the fp32 summation order differs); each case is launched three times and replayed from a
+    CUDA graph, which must give identical bits (the flags are reset by their consumers)."""
+    if case == "linear_bigk_res":
+        x, w, b, r = rnd(2048, 5120), rnd(1280, 5120, scale=5120 ** -0.5, seed=1), rnd(1280, seed=2), rnd(2048, 1280, seed=3)
+        ref = x.float() @ w.float().t() + b.float() + r.float()
+        run = lambda: nv.linear(x, w, b, residual=r)
+    else:
+        NB, H, W, C, N = {"conv_l1": (8, 32, 32, 640, 640), "conv_l2_single_wave": (8, 16, 16, 640, 1280),
+                          "conv_l0_res": (8, 64, 64, 320, 320), "conv_ragged_rowadd_silu": (7, 24, 24, 192, 328)}[case]
+        x = rnd(NB, H, W, C)
+        w4 = rnd(N, C, 3, 3, scale=(9 * C) ** -0.5, seed=1)
+        b = rnd(N, seed=2)
+        wp = w4.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+        xr = x.float().permute(0, 3, 1, 2)
+        if case == "conv_ragged_rowadd_silu":
+            ra = rnd(NB, N, seed=5)
+            ref = F.silu(F.conv2d(xr, w4.float(), b.float(), padding=1) + ra.float()[:, :, None, None])
+            run = lambda: nv.conv3x3(x, wp, b, rowadd=ra, act=nv.ACT_SILU)
+        elif case == "conv_l0_res":
+            r = rnd(NB, H, W, N, seed=3)
+            ref = F.conv2d(xr, w4.float(), b.float(), padding=1) + r.float().permute(0, 3, 1, 2)
+            run = lambda: nv.conv3x3(x, wp, b, residual=r)
+        else:
+            ref = F.conv2d(xr, w4.float(), b.float(), padding=1)
+            run = lambda: nv.conv3x3(x, wp, b)
+        ref = ref.permute(0, 2, 3, 1)
+    nv.set_env_option(None, None)
+    try:
+        nv.set_env_option("gemm_streamk", 0)
+        out0 = run().clone()
+        nv.set_env_option("gemm_streamk", 1)       # opt-in (measured slower than the plain tiling on the UNet's shapes)
+        outs = [run().clone() for _ in range(3)]
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            og = run()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+    finally:
+        nv.set_env_option(None, None)
+    close(out0, ref)
+    close(outs[0], ref)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]) and torch.equal(outs[0], og), "stream-K launches disagree"
+    dmax = (out0.float() - outs[0].float()).abs().max().item()
+    print(f"[stream-K] {case}: max |stream-K - plain tiling| = {dmax:.3e} (ref max {ref.abs().max().item():.2f})")
+    assert dmax <= 4e-3 * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("C", [64, 320])

@@ -1,7 +1,8 @@
-"""A/B of the CTA-pair kernel (cta_group::2, gemm_pair = 1) against the single-CTA kernel on the UNet's 3x3 convs and
-large-K Linears at BASELINE configs[1] (8 CFG samples).  Graph-timed, interleaved rounds, L2-warm operands.
+"""A/B of a GEMM option on the UNet's 3x3 convs and large-K Linears at BASELINE configs[1] (8 CFG samples): by default
+the CTA-pair kernel (cta_group::2, gemm_pair = 1 vs 0); --option gemm_streamk --on 1 --off 0 times the stream-K tail.
+Graph-timed, interleaved rounds, L2-warm operands.
 
-    python tools/gemm_pair_ab.py [--rounds 5] [--reps 10]
+    python tools/gemm_pair_ab.py [--option gemm_pair --on 1 --off 0] [--rounds 5] [--reps 10]
 """
 import argparse
 import json
@@ -29,6 +30,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=5)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--option", default="gemm_pair")
+    ap.add_argument("--on", type=int, default=1)
+    ap.add_argument("--off", type=int, default=0)
     a = ap.parse_args()
     dev = "cuda"
     torch.manual_seed(0)
@@ -53,9 +57,9 @@ def main():
     res_all = {}
     for name, flops, fn in cases:
         graphs = {}
-        for vn, val in (("pair", 1), ("single", 0)):
+        for vn, val in (("pair", a.on), ("single", a.off)):
             nv.set_env_option(None, None)
-            nv.set_env_option("gemm_pair", val)
+            nv.set_env_option(a.option, val)
             graphs[vn] = graph_of(fn, a.reps)
         nv.set_env_option(None, None)
         times = {vn: [] for vn in graphs}
@@ -69,7 +73,7 @@ def main():
                 times[vn].append(e0.elapsed_time(e1) / a.reps * 1000.0)
         med = {vn: sorted(ts)[len(ts) // 2] for vn, ts in times.items()}
         res_all[name] = med
-        print(f"{name:34s} pair {med['pair']:8.2f} us ({flops / med['pair'] / 1e6:7.1f} TF/s)   single {med['single']:8.2f} us "
+        print(f"{name:34s} on {med['pair']:8.2f} us ({flops / med['pair'] / 1e6:7.1f} TF/s)   off {med['single']:8.2f} us "
               f"({flops / med['single'] / 1e6:7.1f} TF/s)   speed-up {med['single'] / med['pair']:.2f}", flush=True)
     print("PAIR_AB_RESULT " + json.dumps(res_all))
 
