@@ -1,20 +1,24 @@
-// Fused flash attention for sm_100a (tcgen05 + TMEM + TMA), used for the UNet / ControlNet
-// self- and cross-attention (attention.py:178-201):  O = softmax(Q K^T * scale) V  per (batch, head)
-// without ever materialising the [N, Nk] score matrix in HBM.
+// Attention kernels for sm_100a (tcgen05 + TMEM + TMA) of the UNet / ControlNet / SeeCoder self- and cross-attention
+// (attention.py:178-201):  O = softmax(Q K^T * scale) V  per (batch, head), the [N, Nk] score matrix never reaches HBM.
 //
+// flash_attn_kernel (any Nk, d <= 192):
 //   CTA = 128 query rows of one (batch, head); KV processed in blocks of 64 keys.
-//   warp 0      : TMA producer (Q once; K / V^T blocks through a 2-stage ring)
-//   warp 1      : tcgen05.mma issuer   S_j = Q K_j^T  (TMEM, double buffered)   O += P_j V_j (TMEM)
-//   warps 2..5  : softmax: thread r owns query row r (TMEM lane r) -> no cross-thread reductions;
-//                 two passes over S_j in TMEM (max, then exp/sum), P_j written to shared memory in
-//                 the K-major 128B-swizzled layout the PV MMA reads, O rescaled in TMEM when the
-//                 running max moves, final O / l written as [B, Nq, heads*d].
-//   Logits are rounded to fp16 like the reference's fp16 score tensor (fp16(q.k * scale)); the softmax
-//   runs on packed half2 (HMNMX2 / HSUB2 / HMUL2 / MUFU.EX2.F16x2, two keys per instruction) and the row
-//   sum l comes for free from the tensor core: row d of the V^T tile is all ones, so column d of the
-//   O accumulator is sum_j p_j (rescaled together with O).
-//   Shared memory is kept small (60-152 KB) so two CTAs share an SM for d <= 80 and overlap each
-//   other's softmax (MUFU/ALU) and MMA phases.
+//   warp 0      : TMA producer (Q once; K through a 2-stage ring, V^T through a 1- or 2-stage ring)
+//   warp 1      : tcgen05.mma issuer   S_j = Q K_j^T  (TMEM)   O += P_j V_j (TMEM)
+//   warps 2..5  : softmax: thread r owns query row r (TMEM lane r) -> no cross-thread reductions; ONE pass over S_j:
+//                 tcgen05.ld of the 64 fp32 logits -> 3-input max chains -> p = ex2(s * scale * log2e - m) in fp32 ->
+//                 fp16 P written to shared memory in the K-major 128B-swizzled layout the PV MMA reads.  The running
+//                 reference exponent m only moves when a block maximum exceeds it by more than 2^8 (lazy rescaling),
+//                 so the TMEM read-modify-write of O is rare; final O / l written as [B, Nq, heads*d].
+//   The row sum l comes for free from the tensor core: row d of the V^T tile is all ones, so column d of the O
+//   accumulator is sum_j p_j of the fp16-rounded probabilities (numerator and denominator stay consistent).
+//   d <= 64: 55 KB of shared memory, 128 TMEM columns, 80 registers -> four CTAs per SM overlap each other's
+//   TMEM-load / MUFU / barrier phases (the kernel is bound by the XU pipe and by the length of the
+//   S -> softmax -> P -> PV hand-off chain, not by the tensor pipe: 4 * d = 160 MMA flops per exponential).
+//   Optional exponent paths for A/B (flash_poly_mod): packed-half MUFU (1), polynomial on the FMA pipe for every n-th pair.
+//
+// xattn_short_kernel (Nk <= 160, d <= 48): persistent single-score-tile kernel for the cross-attention against the 148
+//   context tokens, see below.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -101,7 +105,8 @@ struct FlashCfg {
   static int smem_bytes(int dN) { return Q_BYTES + NKV * K_BYTES + NVS * dN * 128 + NPB * P_BYTES + 1024 + 128; }
 };
 
-// PM > 0: every PM-th pair of exponentials of a key block takes the polynomial path (exp2_poly_h2) instead of MUFU
+// PM > 1: every PM-th pair of exponentials of a key block takes the polynomial path (exp2_poly_h2) instead of MUFU;
+// PM = 1: every pair goes through ONE packed-half MUFU op (ex2.approx.f16x2)
 template <int DCH, int PM>
 __global__ void __launch_bounds__(FA_THREADS, FlashCfg<DCH>::MIN_CTAS)
 flash_attn_kernel(const __grid_constant__ FlashParams p) {
@@ -315,7 +320,13 @@ flash_attn_kernel(const __grid_constant__ FlashParams p) {
       for (int i = 0; i < FA_BKV / 2; ++i) {
         const float t0 = fmaf(__uint_as_float(r[2 * i]), c2, nm);
         const float t1 = fmaf(__uint_as_float(r[2 * i + 1]), c2, nm);
-        if (PM > 0 && (i % (PM > 0 ? PM : 1)) == (PM > 0 ? PM : 1) - 1) {
+        if (PM == 1) {
+          // both exponentials of the pair in ONE MUFU op on packed halves (t rounded to fp16 first: |t| <= 16, so the
+          // exponent error is <= 2^-7 for the smallest terms and <= 2^-11 for the ones that matter - the size of the fp16
+          // rounding of the reference's own score tensor, attention.py:188)
+          const __half2 th = __floats2half2_rn(t0, t1);
+          pk[i] = ex2_f16x2(*reinterpret_cast<const uint32_t*>(&th));
+        } else if (PM > 1 && (i % (PM > 1 ? PM : 2)) == (PM > 1 ? PM : 2) - 1) {
           pk[i] = exp2_poly_h2(t0, t1);
         } else {
           const __half2 h = __floats2half2_rn(fast_exp2(t0), fast_exp2(t1));
@@ -632,7 +643,10 @@ xattn_short_kernel(const __grid_constant__ XsParams p) {
         for (int i = 0; i < 4; ++i) {
           const float t0 = fmaf(__uint_as_float(r[8 * j + 2 * i]), c2, nm);
           const float t1 = fmaf(__uint_as_float(r[8 * j + 2 * i + 1]), c2, nm);
-          if (PM > 0 && ((4 * j + i) % (PM > 0 ? PM : 1)) == (PM > 0 ? PM : 1) - 1) {
+          if (PM == 1) {
+            const __half2 th = __floats2half2_rn(t0, t1);          // packed-half MUFU: two exponentials per op
+            pk[i] = ex2_f16x2(*reinterpret_cast<const uint32_t*>(&th));
+          } else if (PM > 1 && ((4 * j + i) % (PM > 1 ? PM : 2)) == (PM > 1 ? PM : 2) - 1) {
             pk[i] = exp2_poly_h2(t0, t1);
           } else {
             const __half2 h = __floats2half2_rn(fast_exp2(t0), fast_exp2(t1));
@@ -782,6 +796,7 @@ extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, 
     const int smem = xs_smem_bytes((d + 16) & ~15);
     const int pm = option("flash_poly_mod", FLASH_POLY_MOD_DEFAULT);
     if (pm == 4) return launch_xattn_short<4>(x, grid, smem, st);
+    if (pm == 1) return launch_xattn_short<1>(x, grid, smem, st);
     return launch_xattn_short<0>(x, grid, smem, st);
   }
   FlashParams p;
@@ -799,6 +814,7 @@ extern "C" PFD_API int pfd_flash_attn_strided_f16(const void* q, const void* k, 
   if (d <= 64) {
     // d <= 64 is MUFU-bound: a share of the exponentials goes to the FMA pipe ("flash_poly_mod": every n-th pair)
     const int pm = option("flash_poly_mod", FLASH_POLY_MOD_DEFAULT);
+    if (pm == 1) return launch_flash<1, 1>(p, grid, st);
     if (pm == 2) return launch_flash<1, 2>(p, grid, st);
     if (pm == 3) return launch_flash<1, 3>(p, grid, st);
     if (pm == 4) return launch_flash<1, 4>(p, grid, st);

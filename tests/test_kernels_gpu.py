@@ -531,12 +531,12 @@ def test_flash_attention_fused_qk_swapped_vt(nv, B, heads, N, d):
     close(o, ref, rtol=8e-3, atol=4e-3)
 
 
-@pytest.mark.parametrize("pm", [2, 3, 4])
+@pytest.mark.parametrize("pm", [1, 2, 3, 4])
 @pytest.mark.parametrize("B,heads,Nq,Nk,d,qscale", [(2, 8, 4096, 4096, 40, 1.0), (2, 8, 1024, 148, 40, 1.0),
                                                    (1, 4, 300, 200, 64, 4.0), (1, 2, 128, 77, 8, 1.0)])
 def test_flash_attention_polynomial_exp2(nv, pm, B, heads, Nq, Nk, d, qscale):
-    """flash_poly_mod = n: every n-th pair of exponentials is computed on the FMA pipe (packed-half2 Cody-Waite +
-    degree-3 polynomial) instead of MUFU.  Same tolerance as the MUFU path; qscale = 4 makes peaked rows (logit
+    """flash_poly_mod = n > 1: every n-th pair of exponentials is computed on the FMA pipe (packed-half2 Cody-Waite +
+    degree-3 polynomial) instead of MUFU; n = 1: every pair in one packed-half MUFU op (ex2.approx.f16x2).  Same tolerance as the MUFU path; qscale = 4 makes peaked rows (logit
     range ~ +-30: exercises the 2^n scaling, the t < -15 flush and the lazy-rescale headroom)."""
     g = torch.Generator().manual_seed(pm * 100 + Nq)
     q = (qscale * torch.randn((B * heads, Nq, d), generator=g)).cuda().half()
@@ -570,4 +570,4 @@ def test_flash_attention_polynomial_exp2(nv, pm, B, heads, Nq, Nk, d, qscale):
     e0 = ((out0.float() - ref).pow(2).mean() / ref.pow(2).mean()).sqrt().item()
     e1 = ((out1.float() - ref).pow(2).mean() / ref.pow(2).mean()).sqrt().item()
     print(f"[flash poly] pm={pm} N={Nq}x{Nk} d={d}: rel rms MUFU {e0:.2e}  poly {e1:.2e}")
-    assert e1 < max(2.0 * e0, 1.5e-3)
+    assert e1 < (3e-3 if pm == 1 else max(2.0 * e0, 1.5e-3))      # pm = 1: exponent argument rounded to fp16 (2^-8 abs near t = 8)

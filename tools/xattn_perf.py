@@ -46,11 +46,11 @@ def main():
         vt[:, :, :Nk] = torch.randn(B * H, d, Nk, device=dev).half()
         out = torch.empty(B, Nq, H * d, device=dev, dtype=torch.float16)
         run = lambda: nv.flash_attn(q, k, vt, B=B, heads=H, Nq=Nq, Nk=Nk, scale=d ** -0.5, out=out)
-        variants = {"generic": {"xattn_short": 0}, "short": {}, "short poly/4": {"flash_poly_mod": 4},
+        variants = {"generic": {"xattn_short": 0}, "short": {}, "short poly/4": {"flash_poly_mod": 4}, "short f16x2": {"flash_poly_mod": 1},
                     "generic poly/4": {"xattn_short": 0, "flash_poly_mod": 4}}
         if not (Nk <= 160 and d <= 48):
-            variants = {"generic": {}, "generic poly/4": {"flash_poly_mod": 4}, "generic poly/3": {"flash_poly_mod": 3},
-                        "generic poly/2": {"flash_poly_mod": 2}}
+            variants = {"generic": {}, "generic f16x2": {"flash_poly_mod": 1}, "generic poly/4": {"flash_poly_mod": 4},
+                        "generic poly/3": {"flash_poly_mod": 3}}
         graphs = {}
         for vn, opts in variants.items():
             nv.set_env_option(None, None)
