@@ -188,9 +188,10 @@ __device__ __forceinline__ void sk_range(const GemmParams& p, int c, int G, int&
   u0 = (int)(U * c / G);
   u1 = (int)(U * (c + 1) / G);
 }
+template <bool SK>
 __device__ __forceinline__ bool gemm_work(const GemmParams& p, int wi, int total_tiles, WorkItem& w) {
   const int G = gridDim.x, c = blockIdx.x;
-  if (p.sk_R == 0) {
+  if (!SK || p.sk_R == 0) {
     const int work = c + wi * G;
     if (work >= total_tiles * p.splits) return false;
     w.tile = work % total_tiles;
@@ -265,7 +266,7 @@ __device__ __forceinline__ void st_release_gpu(int* ptr, int v) {
 // st.shared (conflict-free in the swizzled layout) -> fence.proxy.async -> one lane issues the TMA store.
 // Out-of-raster rows and columns >= N are clipped by the TMA unit, so there is no per-row predicate, no
 // 64-bit address arithmetic and no global load/store instruction left in the loop.
-template <int BN>
+template <int BN, bool SK>
 __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const EpiTile& e, uint32_t& res_phase) {
   const int q = e.q, lane = e.lane, tx = e.tx, ty = e.ty, tn = e.tn, cbeg = e.cbeg, n32 = e.n32;
   const bool tail16 = e.tail16, has_res = e.has_res, valid = e.valid;
@@ -281,7 +282,7 @@ __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const Ep
   for (int i = 0; i < n32; ++i) live32 += (col_base + cbeg + 32 * i < n_lim) ? 1 : 0;
   const bool live16 = tail16 && (col_base + cbeg + 32 * n32 < n_lim);
   const uint32_t rb_addr = e.rbar;
-  if (e.sk_mode == 1) {
+  if (SK && e.sk_mode == 1) {
     // ---- stream-K contributor: raw fp32 accumulators of this CTA's K range -> sk_ws[slot][row][col], then publish
     // partial-tile layout: private to the (contributor warp, owner warp) pair that share a tile position, so it is chosen
     // for the memory system, not for humans: [slot][warp][16-byte group g of the warp's columns][lane] -> every
@@ -316,7 +317,7 @@ __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const Ep
   // accumulator before the normal epilogue.  Contributor cc used slot 2cc if its range STARTS inside this tile
   // (its tail part) and slot 2cc + 1 if it spilled over from the previous tile (its head part).
   int nsrc = 0, src_slot[6];
-  if (e.sk_mode == 2) {
+  if (SK && e.sk_mode == 2) {
     const int G = gridDim.x;
     const int tstart = e.sk_t * p.num_kb;
     for (int cc = (int)blockIdx.x - 1; cc >= 0 && nsrc < 6; --cc) {
@@ -359,7 +360,7 @@ __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const Ep
     uint32_t r[32];
     tmem_ld32(taddr + c0, r);
     tmem_ld_wait();
-    for (int j = 0; j < nsrc; ++j) {
+    for (int j = 0; SK && j < nsrc; ++j) {
       const uint4* src = reinterpret_cast<const uint4*>(p.sk_ws) +
                          (((long long)src_slot[j] * EPI_WARPS + e.stg_warp) * (BN / 8) + i * 8) * 32 + lane;
 #pragma unroll
@@ -424,7 +425,7 @@ __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const Ep
     uint32_t r[16];
     tmem_ld16(taddr + c0, r);
     tmem_ld_wait();
-    for (int j = 0; j < nsrc; ++j) {
+    for (int j = 0; SK && j < nsrc; ++j) {
       const uint4* src = reinterpret_cast<const uint4*>(p.sk_ws) +
                          (((long long)src_slot[j] * EPI_WARPS + e.stg_warp) * (BN / 8) + n32 * 8) * 32 + lane;
 #pragma unroll
@@ -482,7 +483,9 @@ __device__ __forceinline__ void tma_store_epilogue(const GemmParams& p, const Ep
 // LEAN = false keeps the general path (element-strided outputs such as V^T, split-K partials).
 // TMAE = true (implies LEAN, plain channel-last output, no GEGLU / split-K): the tile leaves through TMA stores and the
 // residual arrives through TMA loads (see the epilogue).
-template <int BN, bool LEAN, bool TMAE>
+// SK = true (implies TMAE): stream-K tail enabled (gemm_work / epilogue modes); a separate instantiation because the extra
+// epilogue state costs the plain kernel 2.5 % (152 vs 140 registers + the work-item arithmetic in all three roles).
+template <int BN, bool LEAN, bool TMAE, bool SK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN, TMAE>;
@@ -554,7 +557,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       WorkItem w;
-      for (int wi = 0; gemm_work(p, wi, total_tiles, w); ++wi) {
+      for (int wi = 0; gemm_work<SK>(p, wi, total_tiles, w); ++wi) {
         const int tile = w.tile;
         const int kb_begin = w.kb0, kb_end = w.kb1;
         const int n_tile = tile % p.n_tiles;
@@ -598,7 +601,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       WorkItem w;
-      for (int it = 0; gemm_work(p, it, total_tiles, w); ++it) {
+      for (int it = 0; gemm_work<SK>(p, it, total_tiles, w); ++it) {
         const int as = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         const int nkb = w.kb1 - w.kb0;
@@ -646,7 +649,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     const bool plain_cols = p.cdiv >= p.N;  // no head split: column offset = col * so_c0
     uint32_t res_phase = 0;                 // TMAE: parity of this warp's residual barrier
     WorkItem w;
-    for (int it = 0; gemm_work(p, it, total_tiles, w); ++it) {
+    for (int it = 0; gemm_work<SK>(p, it, total_tiles, w); ++it) {
       const int tile = w.tile;
       const int split = w.slot;
       const int as = it & 1;
@@ -784,7 +787,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           e.stg = stg; e.rbar = res_bar(warp - 2); e.tfull = tfull_bar(as); e.aph = aph; e.taddr = taddr; e.sbias = sbias;
           e.alpha = alpha; e.act = act; e.rowadd_row = rowadd_row;
           e.sk_mode = w.mode; e.sk_slot = w.slot; e.sk_t = w.tile - p.sk_dp_tiles; e.sk_kb0 = w.kb0; e.stg_warp = warp - 2;
-          tma_store_epilogue<BN>(p, e, res_phase);
+          tma_store_epilogue<BN, SK>(p, e, res_phase);
           tc_fence_before();
           mbar_arrive(tempty_bar(as));
           continue;
@@ -1367,7 +1370,7 @@ gemm_tc2_kernel(const __grid_constant__ GemmParams p) {
         const float b = (p.bias != nullptr && c < p.N) ? __half2float(__ldg(p.bias + c)) : 0.f;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(e.sbias + et * 4), "f"(b) : "memory");
       }
-      tma_store_epilogue<BN>(p, e, res_phase);
+      tma_store_epilogue<BN, false>(p, e, res_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(tempty_bar(as));
@@ -1539,17 +1542,17 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
 
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
-template <int BN, bool LEAN, bool TMAE>
+template <int BN, bool LEAN, bool TMAE, bool SK = false>
 static int launch_gemm_t(const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, TMAE>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN, TMAE>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, LEAN, TMAE, SK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error("cudaFuncSetAttribute(gemm BN=%d): %s", BN, cudaGetErrorString(e));
     attr_done = true;
   }
-  launch_k(gemm_tc_kernel<BN, LEAN, TMAE>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
+  launch_k(gemm_tc_kernel<BN, LEAN, TMAE, SK>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, p);
   return check_launch("pfd_gemm_f16");
 }
 
@@ -1629,6 +1632,7 @@ static int launch_gemm(GemmParams& p, int grid, cudaStream_t stream, const pfd_g
             p.taps[0], p.stride, p.act, p.bias != nullptr, p.residual != nullptr, p.rowadd != nullptr, BN, (int)lean,
             p.splits, grid, p.b_batched, p.vec_ok, (int)(p.cdiv >= p.N), (int)tmae, p.sk_R);
   if constexpr (BN <= 192) {
+    if (tmae && p.sk_R > 0) return launch_gemm_t<BN, true, true, true>(p, grid, stream);
     if (tmae) return launch_gemm_t<BN, true, true>(p, grid, stream);
   }
   return lean ? launch_gemm_t<BN, true, false>(p, grid, stream) : launch_gemm_t<BN, false, false>(p, grid, stream);

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 
-net = bench.synth_cpu_state().half()
+net = bench.synth_net(bench.CONFIGS[2]).half()
 net.to("cuda")
 B, L = 4, 64
 torch.manual_seed(0)
