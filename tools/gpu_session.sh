@@ -1,11 +1,5 @@
 mkdir -p gpurun_out
-(timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q 2>&1 | tail -3) > gpurun_out/r2_t_kernels3.log 2>&1; tail -2 gpurun_out/r2_t_kernels3.log
-: > gpurun_out/r2_cmp_libs2.log
-for i in 1 2 3; do
-  for lib in r2start 1f0fec5 HEAD; do
-    if [ $lib = HEAD ]; then L=$PWD/pfd_b200/libpfd_b200.so; else L=$PWD/tools/oldlib/libpfd_b200_$lib.so; fi
-    echo "== $lib round $i" >> gpurun_out/r2_cmp_libs2.log
-    PFD_B200_LIB=$L timeout 200 python tools/ab_unet.py --rounds 4 --reps 20 2>&1 | grep "^default" >> gpurun_out/r2_cmp_libs2.log
-  done
-done
-cat gpurun_out/r2_cmp_libs2.log
+(timeout 400 python -m pytest tests/test_split_gpu.py -q -s 2>&1 | tail -6) > gpurun_out/r2_t_split.log 2>&1; tail -4 gpurun_out/r2_t_split.log
+timeout 400 python bench.py --gpus 2 --no-cpu-baseline --no-gpu-reference > gpurun_out/r2_bench_2gpu_weak.json 2> gpurun_out/r2_bench_2gpu_weak.err; cut -c1-250 gpurun_out/r2_bench_2gpu_weak.json
+timeout 400 python bench.py --gpus 2 --split --batch 8 --no-cpu-baseline --no-gpu-reference > gpurun_out/r2_bench_2gpu_split.json 2> gpurun_out/r2_bench_2gpu_split.err; cut -c1-250 gpurun_out/r2_bench_2gpu_split.json
+(timeout 400 python -m pytest tests/test_configs_gpu.py tests/test_pipeline_gpu.py -q -s 2>&1 | grep -E "\[parity\]|passed|failed") > gpurun_out/r2_parity_full.log 2>&1; tail -2 gpurun_out/r2_parity_full.log
