@@ -46,7 +46,12 @@ PFD_API const char* pfd_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py: gpu_launches) */
 PFD_API int64_t pfd_launch_count(void);
 /* Run-time tuning switches, so that variants can be A/B-timed inside one process (tools/ab_unet.py); name == NULL
- * resets all of them to the built-in defaults.  Unknown names are stored and ignored. */
+ * resets all of them to the built-in defaults.  Unknown names are stored and ignored.  Known names (default):
+ *   gemm_tma_epi (1)   TMA-store epilogue of pfd_gemm_f16 for plain channel-last outputs (0 = register epilogue)
+ *   gemm_pair (0)      1 = CTA-pair kernel (cta_group::2) for long-K contractions, 2 = wherever applicable
+ *   gemm_streamk (0)   stream-K tail of the persistent GEMM
+ *   xattn_short (1)    persistent single-score-tile kernel of pfd_flash_attn_* for Nk <= 160, d <= 48
+ *   flash_poly_mod (0) exponent path of the attention softmax: 1 = packed-half MUFU, n > 1 = every n-th pair on the FMA pipe */
 PFD_API int pfd_set_option(const char* name, int32_t value);
 
 /*
@@ -210,6 +215,9 @@ PFD_API int pfd_patch_merge_gather_f16(const void* x, int32_t B, int32_t H, int3
  *   q  [B*heads, q_rows, d]   (first Nq rows valid)      k [B*heads, k_rows, d] (first Nk rows valid)
  *   vt [B*heads, d, vt_pitch] (V transposed, first Nk columns valid)
  *   out element (b, i, h, c) at  b*o_sb + i*o_sq + h*d + c.       d % 8 == 0, d <= 192.
+ * Nk <= 160 with d <= 48 (the cross-attention against the 148 SeeCoder context tokens at the UNet's d = 40 level,
+ * attention.py:178-201 with `context`) runs a persistent kernel whose single score tile holds every key (exact row
+ * maximum, no online softmax); everything else the 64-key-block flash kernel.
  */
 PFD_API int pfd_flash_attn_f16(const void* q, const void* k, const void* vt, void* out, int32_t B,
                                int32_t heads, int32_t Nq, int32_t Nk, int32_t d, int32_t q_rows,

@@ -9,10 +9,10 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 this package; the product (pfd_b200/) never does.
 
 Pinning: the reference ships no tests or golden vectors.  The oracle is pinned by
-tools/validate_oracle.py, which imports the unmodified reference from /root/reference in the build
-container, loads identical synthetic weights into both and compares every stage; the vectors it
-produces are committed under tests/golden/ (tools/make_golden.py) and re-checked by
-tests/test_oracle_golden.py on any machine.
+tools/make_golden.py (+ tools/make_golden_configs.py for the BASELINE config sizes), which import the
+unmodified reference from /root/reference in the build container (tools/ref_harness.py), load identical
+synthetic weights into both and compare every stage (tests/golden/oracle_pin_report.json); the reference's
+outputs are committed under tests/golden/ and re-checked by tests/test_oracle_golden.py on any machine.
 """
 from __future__ import annotations
 
